@@ -1,0 +1,167 @@
+/*
+ * yolact_b200.h -- C ABI of libyolact_b200.so: the B200-native (sm_100a) YOLACT hot path.
+ *
+ * The reference (feiyuhuahuo/Yolact_minimal @ d920c05) is pure Python/PyTorch plus one Cython
+ * file; it has no FFI.  Its drop-in boundary is three Python import points:
+ *     modules/yolact.py:141-164      Yolact.forward            -> yb_net_forward / yb_net_detect_host
+ *     utils/output_utils.py:126-163  nms (+ fast_nms :11-43, traditional_nms :84-123)
+ *                                                               -> yb_detect
+ *     utils/output_utils.py:200-233  after_nms (+ box_utils.py:147-168 crop)
+ *                                                               -> yb_mask_assemble
+ *     cython_nms.pyx:24-74           nms(dets, thresh)          -> yb_hard_nms / yb_hard_nms_host
+ * The Python package yolact_minimal_b200 mirrors those import points and binds this library
+ * through ctypes (INTEGRATION.md shows the stubs).  Signatures use plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every entry point returns a yb_status (0 = ok, <0 = error); yb_last_error() returns a
+ *     thread-local message for the last failure.  Nothing here falls back to a CPU path.
+ *   - pointers are DEVICE pointers unless the function name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
+ *     points are asynchronous on that stream; *_host entry points synchronise before returning.
+ *   - all tensors are dense, row-major, float32 unless stated.
+ */
+#ifndef YOLACT_B200_H_
+#define YOLACT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define YB_API __attribute__((visibility("default")))
+#else
+#define YB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  YB_OK = 0,
+  YB_ERR_INVALID = -1,      /* bad argument */
+  YB_ERR_CUDA = -2,         /* CUDA runtime / driver failure */
+  YB_ERR_UNSUPPORTED = -3,  /* shape or option outside what the kernels are built for */
+  YB_ERR_STATE = -4         /* call order (e.g. forward before finalize) */
+} yb_status;
+
+#define YB_VERSION 100
+
+YB_API int yb_version(void);
+YB_API const char* yb_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+YB_API uint64_t yb_launch_count(void);
+/* sm_count / compute capability of the current device */
+YB_API int yb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Post-process: score filter + SSD box decode + Fast-NMS (or per-class greedy NMS) + top-k.
+ * Replaces utils/output_utils.py:126-163 nms(), :11-43 fast_nms(), :84-123 traditional_nms().
+ * Batched over images (the reference is batch-1 only: output_utils.py:127-130).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  float score_thr;    /* cfg.nms_score_thre  (config.py:122)  keep anchor iff max_fg_score >  thr */
+  float iou_thr;      /* cfg.nms_iou_thre    (config.py:123)  Fast: keep iff max IoU <= thr; hard: suppress iff >= thr */
+  int top_k;          /* cfg.top_k           (config.py:124)  <= 256 */
+  int max_det;        /* cfg.max_detections  (config.py:125)  <= 256 */
+  int num_classes;    /* incl. background column 0 (81) */
+  int coef_dim;       /* 32 */
+  int traditional;    /* cfg.traditional_nms: 0 = Fast-NMS, 1 = per-class greedy NMS in pixel coords */
+  float img_size;     /* cfg.img_size, only used when traditional != 0 */
+} yb_detect_params;
+
+YB_API size_t yb_detect_workspace_bytes(int batch, int num_anchors, const yb_detect_params* p);
+
+/* cls [B,A,C] post-softmax, box [B,A,4], coef [B,A,K], anchors [A,4] (cx,cy,w,h).
+ * Outputs (all [B,max_det,...], rows >= out_count[b] are zero-filled):
+ *   out_count [B] int32, out_class [B,max_det] int32 (0-based fg class),
+ *   out_anchor [B,max_det] int32, out_score [B,max_det], out_box [B,max_det,4] corner form in
+ *   [0,1], out_coef [B,max_det,K] (may be NULL). */
+YB_API int yb_detect(const float* cls, const float* box, const float* coef, const float* anchors,
+              int batch, int num_anchors, const yb_detect_params* p,
+              void* workspace, size_t workspace_bytes,
+              int32_t* out_count, int32_t* out_class, int32_t* out_anchor,
+              float* out_score, float* out_box, float* out_coef, void* stream);
+
+/* Same call with HOST buffers: allocates/copies/synchronises internally (the nms() a Python
+ * or C caller with numpy arrays would make).  */
+YB_API int yb_detect_host(const float* cls, const float* box, const float* coef, const float* anchors,
+                   int batch, int num_anchors, const yb_detect_params* p,
+                   int32_t* out_count, int32_t* out_class, int32_t* out_anchor,
+                   float* out_score, float* out_box, float* out_coef);
+
+/* ------------------------------------------------------------------------------------------
+ * Greedy hard NMS -- replaces cython_nms.pyx:24-74 nms(dets, thresh).
+ * dets [n,5] (x1,y1,x2,y2,score) in pixels; '+1' areas; suppress iff ovr >= thresh.
+ * out_keep [n] uint8 flags in ORIGINAL order (the reference returns np.where(flag)[0]).
+ * ---------------------------------------------------------------------------------------- */
+YB_API int yb_hard_nms(const float* dets, int n, float thresh, uint8_t* out_keep, void* stream);
+YB_API int yb_hard_nms_host(const float* dets, int n, float thresh, uint8_t* out_keep);
+
+/* ------------------------------------------------------------------------------------------
+ * Mask assembly -- replaces utils/output_utils.py:217-231 (after_nms) + box_utils.py:147-168.
+ *   masks = sigmoid(proto[P,P,K] @ coef[d,K]^T); crop to box (+1 px pad); bilinear resize to
+ *   max(h,w)^2 (align_corners=False); > 0.5; slice to h x w; boxes*max(h,w) -> int32 (trunc).
+ * proto [P,P,K], coef [d,K], box [d,4]; out_mask [d,img_h,img_w] (uint8 0/1 when
+ * mask_f32 == 0, float32 0/1 otherwise -- the reference's dtype); out_box_px [d,4] int32.
+ * workspace: d*P*P floats.
+ * ---------------------------------------------------------------------------------------- */
+YB_API size_t yb_mask_workspace_bytes(int num_det, int proto_size);
+YB_API int yb_mask_assemble(const float* proto, const float* coef, const float* box, int num_det,
+                     int proto_size, int coef_dim, int img_h, int img_w, int crop, int mask_f32,
+                     void* workspace, size_t workspace_bytes,
+                     void* out_mask, int32_t* out_box_px, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Network: ResNet-50/101 + FPN + ProtoNet + prediction heads (modules/resnet.py,
+ * modules/yolact.py:12-164), eval forward.  Weights are handed over by their reference
+ * state-dict names; BatchNorm is folded at finalize time.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct yb_net yb_net;
+
+typedef enum { YB_PREC_FP32 = 0, YB_PREC_BF16 = 1 } yb_precision;
+
+typedef struct {
+  int depth;          /* 50 or 101 */
+  int img_size;       /* square input side, any value >= 64 (550 and 400 are fine) */
+  int num_classes;    /* incl. background (81) */
+  int num_ratios;     /* len(cfg.aspect_ratios) = 3 */
+  int coef_dim;       /* 32 */
+} yb_net_config;
+
+YB_API int yb_net_create(const yb_net_config* cfg, yb_net** out);
+YB_API void yb_net_destroy(yb_net* net);
+/* number of parameter tensors the net expects, and the name / element count of the i-th */
+YB_API int yb_net_num_params(const yb_net* net);
+YB_API int yb_net_param_info(const yb_net* net, int i, const char** name, int64_t* count);
+/* data: HOST float32 array with `count` elements, reference layout (conv: [Cout,Cin,kh,kw]) */
+YB_API int yb_net_set_param(yb_net* net, const char* name, const float* data, int64_t count);
+/* folds BN, packs weights, allocates the activation arena for up to max_batch images */
+YB_API int yb_net_finalize(yb_net* net, int max_batch, int precision);
+YB_API int yb_net_num_anchors(const yb_net* net);
+YB_API int yb_net_proto_size(const yb_net* net);
+/* anchors [A,4] float32 (cx,cy,w,h), computed in float64 and rounded once (box_utils.py:86-101) */
+YB_API int yb_net_anchors_host(const yb_net* net, float* out);
+YB_API const float* yb_net_anchors_device(const yb_net* net);
+
+/* img [B,3,S,S] NCHW float32 (device).  Outputs (device): cls [B,A,C] softmaxed, box [B,A,4],
+ * coef [B,A,K] (tanh), proto [B,P,P,K] (relu, NHWC) -- Yolact.forward's eval 4-tuple. */
+YB_API int yb_net_forward(yb_net* net, const float* img, int batch,
+                   float* cls, float* box, float* coef, float* proto, void* stream);
+
+/* Debug/parity taps: copy a named intermediate activation ("c3","c4","c5","p3".."p7") of the
+ * last forward into out as NCHW float32 [B,C,H,W] (device). */
+YB_API int yb_net_read_activation(yb_net* net, const char* name, int batch, float* out, int64_t out_count,
+                           int* C, int* H, int* W, void* stream);
+
+/* End-to-end with HOST buffers: H2D(img) -> forward -> detect -> D2H(detections).
+ * img_host [B,3,S,S]; outputs as in yb_detect (host).  The proto/coef needed for masks stay on
+ * the device; yb_net_last_proto() exposes the proto of the last call. */
+YB_API int yb_net_detect_host(yb_net* net, const float* img_host, int batch, const yb_detect_params* p,
+                       int32_t* out_count, int32_t* out_class, int32_t* out_anchor,
+                       float* out_score, float* out_box, float* out_coef);
+YB_API const float* yb_net_last_proto(const yb_net* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLACT_B200_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of libyolact_b200.so (the C ABI in include/yolact_b200.h).
+
+There is no fallback: if the library is missing or a call fails this raises.  Build it with
+`python -m yolact_minimal_b200.build` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libyolact_b200.so')
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+
+class DetectParams(C.Structure):
+    _fields_ = [('score_thr', C.c_float), ('iou_thr', C.c_float), ('top_k', C.c_int), ('max_det', C.c_int),
+                ('num_classes', C.c_int), ('coef_dim', C.c_int), ('traditional', C.c_int), ('img_size', C.c_float)]
+
+
+class NetConfig(C.Structure):
+    _fields_ = [('depth', C.c_int), ('img_size', C.c_int), ('num_classes', C.c_int), ('num_ratios', C.c_int),
+                ('coef_dim', C.c_int)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/yolact_b200.h
+PROTOTYPES = {
+    'yb_version': (C.c_int, []),
+    'yb_last_error': (C.c_char_p, []),
+    'yb_launch_count': (C.c_uint64, []),
+    'yb_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
+    'yb_detect_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.POINTER(DetectParams)]),
+    'yb_detect': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(DetectParams), vp, C.c_size_t,
+                            vp, vp, vp, vp, vp, vp, vp]),
+    'yb_detect_host': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(DetectParams),
+                                 vp, vp, vp, vp, vp, vp]),
+    'yb_hard_nms': (C.c_int, [vp, C.c_int, C.c_float, vp, vp]),
+    'yb_hard_nms_host': (C.c_int, [vp, C.c_int, C.c_float, vp]),
+    'yb_mask_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'yb_mask_assemble': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   vp, C.c_size_t, vp, vp, vp]),
+    'yb_net_create': (C.c_int, [C.POINTER(NetConfig), C.POINTER(vp)]),
+    'yb_net_destroy': (None, [vp]),
+    'yb_net_num_params': (C.c_int, [vp]),
+    'yb_net_param_info': (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
+    'yb_net_set_param': (C.c_int, [vp, C.c_char_p, vp, C.c_int64]),
+    'yb_net_finalize': (C.c_int, [vp, C.c_int, C.c_int]),
+    'yb_net_num_anchors': (C.c_int, [vp]),
+    'yb_net_proto_size': (C.c_int, [vp]),
+    'yb_net_anchors_host': (C.c_int, [vp, vp]),
+    'yb_net_anchors_device': (vp, [vp]),
+    'yb_net_forward': (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp]),
+    'yb_net_read_activation': (C.c_int, [vp, C.c_char_p, C.c_int, vp, C.c_int64, C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int), vp]),
+    'yb_net_detect_host': (C.c_int, [vp, vp, C.c_int, C.POINTER(DetectParams), vp, vp, vp, vp, vp, vp]),
+    'yb_net_last_proto': (vp, [vp]),
+}
+
+_lib = None
+
+
+class YolactB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes library.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise YolactB200Error(
+                f'{LIB_PATH} not found: the CUDA library is not built (run `python -m yolact_minimal_b200.build`). '
+                'There is no CPU fallback.')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)          # AttributeError if the symbol is missing -> loud
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = lib().yb_last_error()
+        raise YolactB200Error(f'{what} failed with status {status}: {msg.decode() if msg else ""}')
+
+
+def launch_count():
+    return int(lib().yb_launch_count())

@@ -1,0 +1,409 @@
+// CUDA-core kernels of the forward: the fp32 parity-mode convolution (also the on-device
+// reference for the tcgen05 path), the stem, and the memory-bound glue layers (max-pool, parity
+// split for stride-2 convs, FPN upsample+add, protonet upsample, head softmax/tanh scatter).
+// All activations use the haloed NHWC layout described in layers.cuh.
+#include "layers.cuh"
+#include <math.h>
+#include <algorithm>
+
+namespace yb {
+
+template <typename T> struct Act;
+template <> struct Act<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Act<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ bool is_halo(long long m, const Geom& g, int& n, int& y, int& x) {
+  const int plane = g.plane();
+  n = (int)(m / plane);
+  const int pos = (int)(m - (long long)n * plane);
+  y = pos / g.Wp();
+  x = pos - y * g.Wp();
+  return y == 0 || y == g.H + 1 || x == 0 || x == g.W + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM convolution on CUDA cores (fp32 accumulate).  64x64 tile, BK=16, 4x4 per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a, long long M) {
+  __shared__ float As[SBK][SBM + 4];
+  __shared__ float Bs[SBK][SBN + 4];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * SBM;
+  const int n0 = blockIdx.y * SBN;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;         // loader: row lr, k offset lk..lk+3
+  const T* in = (const T*)a.in;
+  const T* w = (const T*)a.weight;
+  const int Ktot = a.ntaps * a.Cin;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < a.ntaps; ++t) {
+    const long long arow = m0 + lr + a.tap_shift[t];
+    const bool a_ok = (m0 + lr < M) && arow >= 0 && arow < a.in_rows;
+    const T* ap = in + arow * a.Cin + lk;
+    const T* bp = w + (long long)(n0 + lr) * Ktot + (long long)t * a.Cin + lk;
+    for (int k0 = 0; k0 < a.Cin; k0 += SBK) {
+      float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4];
+      if (a_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) av[q] = Act<T>::ld(ap + k0 + q);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bv[q] = Act<T>::ld(bp + k0 + q);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { As[lk + q][lr] = av[q]; Bs[lk + q][lr] = bv[q]; }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < SBK; ++k) {
+        const float4 af = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 bf = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float ar[4] = {af.x, af.y, af.z, af.w}, br[4] = {bf.x, bf.y, bf.z, bf.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
+  }
+  // epilogue
+  const T* res = (const T*)a.residual;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    int n, y, x;
+    const bool halo = is_halo(m, a.g, n, y, x);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= a.Cout_pad) continue;
+      float v = acc[i][j] + a.bias[c];
+      if (a.out_mode == 0) {
+        if (c >= a.Cout) continue;
+        if (res) v += Act<T>::ld(res + m * a.Cout + c);
+        if (a.relu) v = fmaxf(v, 0.f);
+        Act<T>::st((T*)a.out + m * a.Cout + c, halo ? 0.f : v);
+      } else if (!halo) {
+        if (a.relu) v = fmaxf(v, 0.f);
+        const long long r = ((long long)n * a.g.H + (y - 1)) * a.g.W + (x - 1);
+        ((float*)a.out)[r * a.Cout_pad + c] = v;
+      }
+    }
+  }
+}
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
+  const long long M = (long long)a.B * a.g.plane();
+  dim3 grid((unsigned)((M + SBM - 1) / SBM), (unsigned)ceil_div(a.Cout_pad, SBN));
+  YB_REQUIRE(a.Cin % SBK == 0, YB_ERR_UNSUPPORTED, "conv_simt: Cin=%d not a multiple of %d", a.Cin, SBK);
+  if (a.act_dt == DT_F32) k_conv_simt<float><<<grid, 256, 0, s>>>(a, M);
+  else k_conv_simt<__nv_bfloat16><<<grid, 256, 0, s>>>(a, M);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: conv 7x7 s2 p3 (3->64) + folded BN + ReLU, NCHW fp32 image -> haloed NHWC.
+// One thread = one output pixel x 64 channels; 16x16 pixel tile per block.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST = 16;                       // tile side (output pixels)
+constexpr int SP = ST * 2 + 5;               // input patch side (37)
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_stem(const float* __restrict__ img, const float* __restrict__ w,
+                                              const float* __restrict__ bias, T* __restrict__ out, int S, int H1) {
+  extern __shared__ float sm[];
+  float* s_w = sm;                           // [7*7*3][64]
+  float* s_in = sm + 147 * 64;               // [3][SP][SP+1]
+  const int tid = threadIdx.x, b = blockIdx.z;
+  const int oy0 = blockIdx.y * ST, ox0 = blockIdx.x * ST;
+  for (int i = tid; i < 147 * 64; i += 256) s_w[i] = w[i];
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = tid; i < 3 * SP * SP; i += 256) {
+    const int c = i / (SP * SP), r = (i / SP) % SP, q = i % SP;
+    const int iy = iy0 + r, ix = ix0 + q;
+    float v = 0.f;
+    if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = img[(((size_t)b * 3 + c) * S + iy) * S + ix];
+    s_in[(c * SP + r) * (SP + 1) + q] = v;
+  }
+  __syncthreads();
+  const int py = tid / ST, px = tid % ST;
+  const int oy = oy0 + py, ox = ox0 + px;
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+  for (int r = 0; r < 7; ++r)
+    for (int q = 0; q < 7; ++q)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = s_in[(ci * SP + py * 2 + r) * (SP + 1) + px * 2 + q];
+        const float4* wp = reinterpret_cast<const float4*>(s_w + ((r * 7 + q) * 3 + ci) * 64);
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 ww = wp[c4];
+          acc[c4 * 4 + 0] = fmaf(v, ww.x, acc[c4 * 4 + 0]);
+          acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
+          acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+        }
+      }
+  if (oy < H1 && ox < H1) {
+    T* o = out + (((size_t)b * (H1 + 2) + oy + 1) * (H1 + 2) + ox + 1) * 64;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) Act<T>::st(o + c, fmaxf(acc[c] + bias[c], 0.f));
+  }
+}
+
+template <typename T>
+__global__ void k_zero_halo(T* __restrict__ t, int B, int C, int H) {
+  // zero the 1-pixel frame of a haloed tensor [B][H+2][H+2][C]
+  const int Hp = H + 2;
+  const long long total = (long long)B * (4 * Hp - 4) * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int e = (int)(r % (4 * Hp - 4));
+    const int b = (int)(r / (4 * Hp - 4));
+    int y, x;
+    if (e < Hp) { y = 0; x = e; }
+    else if (e < 2 * Hp) { y = Hp - 1; x = e - Hp; }
+    else if (e < 3 * Hp - 2) { y = e - 2 * Hp + 1; x = 0; }
+    else { y = e - (3 * Hp - 2) + 1; x = Hp - 1; }
+    t[(((size_t)b * Hp + y) * Hp + x) * C + c] = T(0.f);
+  }
+}
+
+int launch_stem(const float* img, const float* w, const float* bias, void* out, int out_dt, int B, int S, int H1,
+                cudaStream_t s) {
+  const size_t smem = (147 * 64 + 3 * SP * (SP + 1)) * sizeof(float);
+  dim3 grid(ceil_div(H1, ST), ceil_div(H1, ST), B);
+  if (out_dt == DT_F32) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_stem<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stem<float><<<grid, 256, smem, s>>>(img, w, bias, (float*)out, S, H1);
+    YB_CHECK_LAUNCH();
+    k_zero_halo<float><<<148, 256, 0, s>>>((float*)out, B, 64, H1);
+  } else {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_stem<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stem<__nv_bfloat16><<<grid, 256, smem, s>>>(img, w, bias, (__nv_bfloat16*)out, S, H1);
+    YB_CHECK_LAUNCH();
+    k_zero_halo<__nv_bfloat16><<<148, 256, 0, s>>>((__nv_bfloat16*)out, B, 64, H1);
+  }
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3 s2 p1 on post-ReLU data (zero halo == -inf padding because everything is >= 0)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_maxpool(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout) {
+  const int Hpi = Hin + 2, Hpo = Hout + 2;
+  const long long total = (long long)B * Hpo * Hpo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int xp = (int)(r % Hpo); r /= Hpo;
+    const int yp = (int)(r % Hpo);
+    const int b = (int)(r / Hpo);
+    float m = 0.f;
+    if (yp >= 1 && yp <= Hout && xp >= 1 && xp <= Hout) {
+      const int y = yp - 1, x = xp - 1;                      // window rows 2y-1..2y+1 -> haloed 2y..2y+2
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int yy = 2 * y + dy, xx = 2 * x + dx;      // haloed coords, always < Hpi because 2*(Hout-1)+2 <= Hin+1
+          m = fmaxf(m, Act<T>::ld(in + (((size_t)b * Hpi + yy) * Hpi + xx) * C + c));
+        }
+    }
+    Act<T>::st(out + i, m);
+  }
+}
+
+int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s) {
+  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  if (dt == DT_F32) k_maxpool<float><<<blocks, 256, 0, s>>>((const float*)in, (float*)out, B, C, Hin, Hout);
+  else k_maxpool<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, C, Hin, Hout);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity split for stride-2 convs: plane (p,q)[y'][x'] = X[2y'+p][2x'+q] (0 outside), y' in
+// [-1, Hout], stored with the OUTPUT's haloed geometry.  nplanes = 4 (3x3 s2) or 1 (1x1 s2).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_phase_split(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout,
+                              int nplanes, long long plane_stride_rows) {
+  const int Hpi = Hin + 2, Hpo = Hout + 2;
+  const long long per_plane = (long long)B * Hpo * Hpo * C;
+  const long long total = per_plane * nplanes;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pl = (int)(i / per_plane);
+    long long r = i - pl * per_plane;
+    const int c = (int)(r % C); r /= C;
+    const int xp = (int)(r % Hpo); r /= Hpo;
+    const int yp = (int)(r % Hpo);
+    const int b = (int)(r / Hpo);
+    const int p = pl >> 1, q = pl & 1;
+    const int iy = 2 * (yp - 1) + p, ix = 2 * (xp - 1) + q;
+    float v = 0.f;
+    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) v = Act<T>::ld(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + c);
+    Act<T>::st(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + c, v);
+  }
+}
+
+int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
+                       long long plane_stride_rows, cudaStream_t s) {
+  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C * nplanes;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  if (dt == DT_F32) k_phase_split<float><<<blocks, 256, 0, s>>>((const float*)in, (float*)out, B, C, Hin, Hout, nplanes, plane_stride_rows);
+  else k_phase_split<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, C, Hin, Hout, nplanes, plane_stride_rows);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FPN top-down: fine += bilinear(coarse -> fine size), align_corners=False (modules/yolact.py:74-80)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(int dst, float scale, bool align, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = align ? scale * (float)dst : fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)src, in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+template <typename T, bool kAdd, bool kAlign>
+__global__ void k_bilinear(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int Hs, int Hd, float scale) {
+  const int Hps = Hs + 2, Hpd = Hd + 2;
+  const long long total = (long long)B * Hpd * Hpd * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int xp = (int)(r % Hpd); r /= Hpd;
+    const int yp = (int)(r % Hpd);
+    const int b = (int)(r / Hpd);
+    const bool halo = yp == 0 || yp == Hd + 1 || xp == 0 || xp == Hd + 1;
+    if (halo) { if (!kAdd) Act<T>::st(dst + i, 0.f); continue; }
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    src_index(yp - 1, scale, kAlign, Hs, y0, y1, ly0, ly1);
+    src_index(xp - 1, scale, kAlign, Hs, x0, x1, lx0, lx1);
+    const T* sb = src + (size_t)b * Hps * Hps * C + c;
+    const float v00 = Act<T>::ld(sb + ((size_t)(y0 + 1) * Hps + x0 + 1) * C), v01 = Act<T>::ld(sb + ((size_t)(y0 + 1) * Hps + x1 + 1) * C);
+    const float v10 = Act<T>::ld(sb + ((size_t)(y1 + 1) * Hps + x0 + 1) * C), v11 = Act<T>::ld(sb + ((size_t)(y1 + 1) * Hps + x1 + 1) * C);
+    float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    if (kAdd) v += Act<T>::ld(dst + i);
+    Act<T>::st(dst + i, v);
+  }
+}
+
+int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, int Hc, int Hf, cudaStream_t s) {
+  const long long total = (long long)B * (Hf + 2) * (Hf + 2) * C;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const float scale = (float)Hc / (float)Hf;
+  if (dt == DT_F32) k_bilinear<float, true, false><<<blocks, 256, 0, s>>>((const float*)coarse, (float*)fine, B, C, Hc, Hf, scale);
+  else k_bilinear<__nv_bfloat16, true, false><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)coarse, (__nv_bfloat16*)fine, B, C, Hc, Hf, scale);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+// protonet: bilinear x2, align_corners=True (modules/yolact.py:43,:51)
+int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hin, cudaStream_t s) {
+  const int Hout = 2 * Hin;
+  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const float scale = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  if (dt == DT_F32) k_bilinear<float, false, true><<<blocks, 256, 0, s>>>((const float*)in, (float*)out, B, C, Hin, Hout, scale);
+  else k_bilinear<__nv_bfloat16, false, true><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, C, Hin, Hout, scale);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// head epilogue: per (image, pixel, anchor) -- one warp -- softmax over the class logits, copy
+// the box regression, tanh the mask coefficients, scattered to the reference's
+// [B, A, C] / [B, A, 4] / [B, A, K] layout (modules/yolact.py:26-31,:155-163).
+// head row layout: [conf: R*C | box: R*4 | coef: R*K | pad]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_head_finalize(const float* __restrict__ head, int ld, int B, int HW, int R, int NC, int K,
+                                                       int anchor_offset, int A_total, float* __restrict__ cls,
+                                                       float* __restrict__ box, float* __restrict__ coef) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)B * HW * R;
+  for (long long wi = warp; wi < total; wi += nwarps) {
+    const int a = (int)(wi % R);
+    const long long pr = wi / R;                  // b*HW + pix
+    const int b = (int)(pr / HW), pix = (int)(pr - (long long)b * HW);
+    const float* row = head + pr * ld;
+    const long long arow = (long long)b * A_total + anchor_offset + (long long)pix * R + a;
+    // softmax over NC logits
+    const float* lg = row + a * NC;
+    float mx = -INFINITY;
+    for (int c = lane; c < NC; c += 32) mx = fmaxf(mx, lg[c]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    for (int c = lane; c < NC; c += 32) sum += expf(lg[c] - mx);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.f / sum;
+    for (int c = lane; c < NC; c += 32) cls[arow * NC + c] = expf(lg[c] - mx) * inv;
+    if (lane < 4) box[arow * 4 + lane] = row[R * NC + a * 4 + lane];
+    for (int k = lane; k < K; k += 32) coef[arow * K + k] = tanhf(row[R * NC + R * 4 + a * K + k]);
+  }
+}
+
+int launch_head_finalize(const float* head, int ld, int B, int HW, int R, int NC, int K, int anchor_offset, int A_total,
+                         float* cls, float* box, float* coef, cudaStream_t s) {
+  const long long total = (long long)B * HW * R;
+  const int blocks = (int)std::min<long long>((total * 32 + 255) / 256, 148LL * 16);
+  k_head_finalize<<<blocks, 256, 0, s>>>(head, ld, B, HW, R, NC, K, anchor_offset, A_total, cls, box, coef);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug tap: haloed NHWC -> dense NCHW fp32
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_read_act(const T* __restrict__ in, int B, int C, int H, float* __restrict__ out) {
+  const int Hp = H + 2;
+  const long long total = (long long)B * C * H * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % H);
+    long long r = i / H;
+    const int y = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    out[i] = Act<T>::ld(in + (((size_t)b * Hp + y + 1) * Hp + x + 1) * C + c);
+  }
+}
+
+int launch_read_activation(const void* in, int dt, int B, int C, int H, float* out, cudaStream_t s) {
+  const long long total = (long long)B * C * H * H;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  if (dt == DT_F32) k_read_act<float><<<blocks, 256, 0, s>>>((const float*)in, B, C, H, out);
+  else k_read_act<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, B, C, H, out);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+}  // namespace yb

@@ -1,0 +1,68 @@
+// Layer-level launchers shared by net.cu, kernels_simt.cu and conv_tc.cu.
+//
+// Activation layout ("haloed NHWC"): a tensor with logical shape [B, C, H, W] is stored as
+// [B, H+2, W+2, C] with a ZERO one-pixel halo, i.e. as a row-major matrix of
+// M = B*(H+2)*(W+2) rows by C columns.  In this layout every convolution tap of a stride-1
+// 3x3 / 1x1 convolution is a constant ROW SHIFT of that matrix (dy*(W+2) + dx), so each conv
+// is a plain GEMM  out[M, Cout] = sum_taps  in[M + shift_t, Cin] * Wt[Cin, Cout]  whose A
+// operand is loaded by 2D TMA tiles at a shifted row coordinate (out-of-range rows are
+// zero-filled by TMA).  Stride-2 convolutions first split their input into 4 parity planes
+// with the OUTPUT geometry (k_phase_split), after which they are again constant row shifts.
+// Every producer writes zeros into the halo rows/columns of its output.
+#pragma once
+#include "common.cuh"
+
+namespace yb {
+
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+static inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+struct Geom {          // geometry of a haloed tensor
+  int H, W;            // valid extent
+  __host__ __device__ int Hp() const { return H + 2; }
+  __host__ __device__ int Wp() const { return W + 2; }
+  __host__ __device__ int plane() const { return Hp() * Wp(); }
+};
+
+constexpr int kMaxTaps = 9;
+
+struct ConvArgs {
+  const void* in;        // haloed NHWC activations (dtype act_dt); for stride-2: parity planes
+  const void* weight;    // packed [Cout_pad][ntaps*Cin], act_dt (fp32 or bf16), BN folded
+  const float* bias;     // [Cout_pad]
+  const void* residual;  // haloed NHWC (act_dt) with Cout channels, or nullptr
+  void* out;             // see out_mode
+  int act_dt;            // DType of in / residual / (out when out_mode == 0)
+  int B;                 // images in this call
+  Geom g;                // geometry of the OUTPUT (== input geometry for stride 1 / parity planes)
+  int Cin, Cout, Cout_pad;
+  int ntaps;
+  int tap_shift[kMaxTaps];   // row shift into `in` per tap (includes parity-plane offsets)
+  int relu;
+  int out_mode;          // 0: haloed NHWC act_dt, halo zeroed;  1: dense fp32 [B*H*W][Cout] (halo rows skipped)
+  long long in_rows;     // total rows addressable in `in` (for bounds checks)
+};
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
+
+// conv_tc.cu: tcgen05 path (bf16 only).  `plan` is an opaque per-layer object holding the TMA
+// descriptors; created once at finalize time.
+struct TcPlan;
+int tc_plan_create(const ConvArgs& a_maxbatch, int max_batch, TcPlan** out);
+void tc_plan_destroy(TcPlan* p);
+int launch_conv_tc(const TcPlan* p, const ConvArgs& a, cudaStream_t s);
+bool tc_supported(const ConvArgs& a);
+
+int launch_stem(const float* img_nchw, const float* w /*[7][7][3][64]*/, const float* bias, void* out, int out_dt,
+                int B, int S, int H1, cudaStream_t s);
+int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s);
+int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
+                       long long plane_stride_rows, cudaStream_t s);
+int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, int Hc, int Hf, cudaStream_t s);
+int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hin, cudaStream_t s);
+int launch_head_finalize(const float* head /*[B*H*W][ld]*/, int ld, int B, int HW, int num_ratios, int num_classes,
+                         int coef_dim, int anchor_offset, int A_total, float* cls, float* box, float* coef,
+                         cudaStream_t s);
+int launch_read_activation(const void* in, int dt, int B, int C, int H, float* out_nchw, cudaStream_t s);
+
+}  // namespace yb

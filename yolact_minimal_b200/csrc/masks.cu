@@ -1,0 +1,139 @@
+// Mask assembly on the GPU.  Replaces utils/output_utils.py:217-231 (after_nms) and
+// utils/box_utils.py:117-132,:147-168 (sanitize_coordinates, crop):
+//   low  = crop(sigmoid(proto[P,P,K] @ coef[d,K]^T))            k_mask_lowres   -> ws[d,P,P]
+//   mask = bilinear(low -> max(h,w)^2, align_corners=False) > 0.5, sliced to h x w   k_mask_resize
+//   boxes_px = int32(trunc(box * max(h,w)))
+// Both kernels are HBM/L2 streaming kernels: proto is read once per 16-detection group (from
+// L2 after the first), the full-resolution mask is written once, coalesced along x.
+#include "common.cuh"
+#include <math.h>
+
+namespace yb {
+
+constexpr int kMaskThreads = 256;
+constexpr int kDetGroup = 16;      // detections per lowres thread (registers hold 16 accumulators)
+constexpr int kMaxK = 64;
+
+// proto pixel per thread; blockIdx.y = detection group
+__global__ void __launch_bounds__(kMaskThreads)
+k_mask_lowres(const float* __restrict__ proto, const float* __restrict__ coef, const float* __restrict__ box,
+              int d, int P, int K, int crop, float* __restrict__ low) {
+  __shared__ float s_coef[kDetGroup][kMaxK];
+  __shared__ float s_x1[kDetGroup], s_x2[kDetGroup], s_y1[kDetGroup], s_y2[kDetGroup];
+  const int g0 = blockIdx.y * kDetGroup;
+  const int ng = min(kDetGroup, d - g0);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < ng * K; e += kMaskThreads) s_coef[e / K][e % K] = coef[(size_t)(g0 + e / K) * K + e % K];
+  if (tid < ng) {
+    // sanitize_coordinates (box_utils.py:124-132), padding = 1, float compares, no rounding
+    const float4 b = reinterpret_cast<const float4*>(box)[g0 + tid];
+    const float fp = (float)P;
+    float xa = __fmul_rn(b.x, fp), xb = __fmul_rn(b.z, fp), ya = __fmul_rn(b.y, fp), yb_ = __fmul_rn(b.w, fp);
+    float x1 = fminf(xa, xb), x2 = fmaxf(xa, xb), y1 = fminf(ya, yb_), y2 = fmaxf(ya, yb_);
+    x1 = __fsub_rn(x1, 1.f); x1 = x1 < 0.f ? 0.f : x1;
+    y1 = __fsub_rn(y1, 1.f); y1 = y1 < 0.f ? 0.f : y1;
+    x2 = __fadd_rn(x2, 1.f); x2 = x2 > fp ? fp : x2;
+    y2 = __fadd_rn(y2, 1.f); y2 = y2 > fp ? fp : y2;
+    s_x1[tid] = x1; s_x2[tid] = x2; s_y1[tid] = y1; s_y2[tid] = y2;
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * kMaskThreads + tid;
+  if (pix >= P * P) return;
+  const int y = pix / P, x = pix - y * P;
+  float acc[kDetGroup];
+#pragma unroll
+  for (int g = 0; g < kDetGroup; ++g) acc[g] = 0.f;
+  const float* pp = proto + (size_t)pix * K;
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const float4 pv = *reinterpret_cast<const float4*>(pp + k0);
+#pragma unroll
+    for (int g = 0; g < kDetGroup; ++g) {
+      acc[g] = fmaf(pv.x, s_coef[g][k0], acc[g]);
+      acc[g] = fmaf(pv.y, s_coef[g][k0 + 1], acc[g]);
+      acc[g] = fmaf(pv.z, s_coef[g][k0 + 2], acc[g]);
+      acc[g] = fmaf(pv.w, s_coef[g][k0 + 3], acc[g]);
+    }
+  }
+  const float fx = (float)x, fy = (float)y;
+#pragma unroll
+  for (int g = 0; g < kDetGroup; ++g) {
+    if (g < ng) {
+      float v = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-acc[g])));
+      if (crop) {
+        const bool in = (fx >= s_x1[g]) && (fx < s_x2[g]) && (fy >= s_y1[g]) && (fy < s_y2[g]);
+        v = in ? v : 0.f;
+      }
+      low[((size_t)(g0 + g) * P + y) * P + x] = v;
+    }
+  }
+}
+
+// ATen upsample_bilinear2d (align_corners=False) source index, fp32 arithmetic
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  src = src < 0.f ? 0.f : src;
+  i0 = min((int)src, in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = __fsub_rn(src, (float)i0);
+  l0 = __fsub_rn(1.f, l1);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kMaskThreads)
+k_mask_resize(const float* __restrict__ low, int d, int P, int ori, int img_h, int img_w, OutT* __restrict__ out) {
+  const int det = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int ox = blockIdx.x * kMaskThreads + threadIdx.x;
+  if (ox >= img_w) return;
+  const float scale = __fdiv_rn((float)P, (float)ori);
+  int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+  bilinear_src(oy, scale, P, y0, y1, ly0, ly1);
+  bilinear_src(ox, scale, P, x0, x1, lx0, lx1);
+  const float* src = low + (size_t)det * P * P;
+  const float v00 = src[y0 * P + x0], v01 = src[y0 * P + x1], v10 = src[y1 * P + x0], v11 = src[y1 * P + x1];
+  // ATen: w_y0 * (w_x0 * v00 + w_x1 * v01) + w_y1 * (w_x0 * v10 + w_x1 * v11)
+  const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
+  const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
+  const float v = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+  out[((size_t)det * img_h + oy) * img_w + ox] = (OutT)(v > 0.5f ? 1 : 0);
+}
+
+__global__ void k_boxes_px(const float* __restrict__ box, int n4, float ori, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) out[i] = (int32_t)__fmul_rn(box[i], ori);      // .int() truncates toward zero
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" size_t yb_mask_workspace_bytes(int num_det, int proto_size) {
+  if (num_det <= 0 || proto_size <= 0) return 0;
+  return (size_t)num_det * proto_size * proto_size * sizeof(float);
+}
+
+extern "C" int yb_mask_assemble(const float* proto, const float* coef, const float* box, int num_det,
+                                int proto_size, int coef_dim, int img_h, int img_w, int crop, int mask_f32,
+                                void* workspace, size_t workspace_bytes, void* out_mask, int32_t* out_box_px,
+                                void* stream_) {
+  YB_REQUIRE(num_det >= 0, YB_ERR_INVALID, "yb_mask_assemble: num_det=%d", num_det);
+  if (num_det == 0) return YB_OK;
+  YB_REQUIRE(proto && coef && box && workspace && out_mask && out_box_px, YB_ERR_INVALID, "yb_mask_assemble: NULL pointer argument");
+  YB_REQUIRE(proto_size > 0 && img_h > 0 && img_w > 0, YB_ERR_INVALID, "yb_mask_assemble: bad sizes P=%d h=%d w=%d", proto_size, img_h, img_w);
+  YB_REQUIRE(coef_dim > 0 && coef_dim <= kMaxK && coef_dim % 4 == 0, YB_ERR_UNSUPPORTED, "yb_mask_assemble: coef_dim=%d (need multiple of 4, <= %d)", coef_dim, kMaxK);
+  YB_REQUIRE(workspace_bytes >= yb_mask_workspace_bytes(num_det, proto_size), YB_ERR_INVALID, "yb_mask_assemble: workspace too small");
+  YB_REQUIRE(num_det <= 65535 && img_h <= 65535, YB_ERR_UNSUPPORTED, "yb_mask_assemble: num_det/img_h exceed grid limits");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int P = proto_size, ori = img_h > img_w ? img_h : img_w;
+  float* low = (float*)workspace;
+  k_mask_lowres<<<dim3(ceil_div(P * P, kMaskThreads), ceil_div(num_det, kDetGroup)), kMaskThreads, 0, stream>>>(
+      proto, coef, box, num_det, P, coef_dim, crop, low);
+  YB_CHECK_LAUNCH();
+  dim3 grid(ceil_div(img_w, kMaskThreads), img_h, num_det);
+  if (mask_f32) k_mask_resize<float><<<grid, kMaskThreads, 0, stream>>>(low, num_det, P, ori, img_h, img_w, (float*)out_mask);
+  else k_mask_resize<uint8_t><<<grid, kMaskThreads, 0, stream>>>(low, num_det, P, ori, img_h, img_w, (uint8_t*)out_mask);
+  YB_CHECK_LAUNCH();
+  k_boxes_px<<<ceil_div(num_det * 4, 128), 128, 0, stream>>>(box, num_det * 4, (float)ori, out_box_px);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}

@@ -1,0 +1,614 @@
+// Host side of the network: parameter table with the reference's state-dict names, BN folding
+// and weight packing, the flat layer program (modules/resnet.py:86-98 + modules/yolact.py:73-89,
+// :49-53, :26-31, :141-164 restated as a list of GEMM-shaped convs on haloed NHWC tensors),
+// a liveness-based activation arena, and the yb_net_* C ABI.
+#include "layers.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace yb;
+
+namespace {
+
+struct Param {
+  std::string name;
+  int64_t count;
+  std::vector<float> data;
+  bool set = false;
+};
+
+struct ActBuf {
+  int C = 0, H = 0;            // logical channels / valid side (square feature maps)
+  int planes = 1;              // >1 for parity-split tensors
+  int dt = DT_F32;
+  size_t bytes = 0;            // for max_batch
+  int first = 0, last = 0;     // op indices (liveness)
+  int slot = -1;
+  bool dense_f32 = false;      // dense [B*H*W][C] fp32 scratch (head outputs)
+};
+
+enum OpKind { OP_STEM, OP_POOL, OP_SPLIT, OP_CONV, OP_UPADD, OP_UP2X, OP_HEADFIN };
+enum ExtOut { EXT_NONE = 0, EXT_PROTO = 1 };
+
+struct ConvW {                 // one packed convolution
+  std::string wname, bname, bnname;   // weight / bias / batch-norm prefix ("" if absent)
+  std::vector<std::string> cat;        // head: concatenated convs (conf|box|coef)
+  int Cin = 0, Cout = 0, Cout_pad = 0, k = 1;
+  void* d_w = nullptr;         // packed [Cout_alloc][k*k*Cin] in act dtype
+  float* d_b = nullptr;        // [Cout_alloc]
+};
+
+struct Op {
+  OpKind kind;
+  int in = -1, out = -1, res = -1;
+  int conv = -1;               // index into convs
+  int stride = 1, relu = 0, out_mode = 0, ext = EXT_NONE;
+  int level = 0;               // head level
+  TcPlan* tc = nullptr;
+};
+
+}  // namespace
+
+struct yb_net {
+  yb_net_config cfg{};
+  std::vector<Param> params;
+  std::map<std::string, int> pidx;
+  std::vector<ActBuf> acts;
+  std::vector<ConvW> convs;
+  std::vector<Op> ops;
+  std::map<std::string, int> taps;          // debug taps: name -> act
+  std::vector<void*> slots;
+  std::vector<size_t> slot_bytes;
+  bool finalized = false;
+  int max_batch = 0, precision = 0, act_dt = DT_F32;
+  int H1 = 0, H2 = 0;
+  int level_size[5]{}, level_off[5]{};
+  int A = 0, P = 0;
+  std::vector<float> anchors;               // [A,4]
+  float* d_anchors = nullptr;
+  float* d_stem_w = nullptr;                // [7][7][3][64]
+  float* d_stem_b = nullptr;
+  // scratch for yb_net_detect_host
+  float *d_img = nullptr, *d_cls = nullptr, *d_box = nullptr, *d_coef = nullptr, *d_proto = nullptr;
+  void* d_ws = nullptr; size_t ws_bytes = 0;
+  int32_t *d_cnt = nullptr, *d_ocls = nullptr, *d_oanc = nullptr; float *d_osc = nullptr, *d_obox = nullptr, *d_ocoef = nullptr;
+  int host_batch = 0; int host_maxdet = 0;
+  cudaStream_t own_stream = nullptr;
+
+  int add_param(const std::string& n, int64_t count) {
+    Param p; p.name = n; p.count = count;
+    pidx[n] = (int)params.size();
+    params.push_back(std::move(p));
+    return (int)params.size() - 1;
+  }
+  const std::vector<float>& P_(const std::string& n) const { return params[pidx.at(n)].data; }
+};
+
+namespace {
+
+int new_act(yb_net* net, int C, int H, int planes = 1, bool dense_f32 = false) {
+  ActBuf a; a.C = C; a.H = H; a.planes = planes; a.dense_f32 = dense_f32;
+  net->acts.push_back(a);
+  return (int)net->acts.size() - 1;
+}
+
+int new_conv(yb_net* net, const std::string& wname, const std::string& bname, const std::string& bnname, int Cin, int Cout, int k) {
+  ConvW c; c.wname = wname; c.bname = bname; c.bnname = bnname; c.Cin = Cin; c.Cout = Cout; c.Cout_pad = Cout; c.k = k;
+  net->add_param(wname, (int64_t)Cout * Cin * k * k);
+  if (!bname.empty()) net->add_param(bname, Cout);
+  if (!bnname.empty()) {
+    for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) net->add_param(bnname + s, Cout);
+  }
+  net->convs.push_back(c);
+  return (int)net->convs.size() - 1;
+}
+
+// appends [split +] conv; returns output act
+int add_conv(yb_net* net, int in, int conv, int stride, int relu, int res = -1, int out_mode = 0, int ext = EXT_NONE, int out_act = -1) {
+  const ConvW& c = net->convs[conv];
+  const int Hin = net->acts[in].H;
+  int Hout = Hin;
+  int src = in;
+  if (stride == 2) {
+    Hout = (Hin - 1) / 2 + 1;
+    const int planes = c.k == 3 ? 4 : 1;
+    src = new_act(net, c.Cin, Hout, planes);
+    Op sp; sp.kind = OP_SPLIT; sp.in = in; sp.out = src;
+    net->ops.push_back(sp);
+  }
+  int out = out_act;
+  if (out < 0 && ext == EXT_NONE) out = new_act(net, out_mode == 1 ? c.Cout_pad : c.Cout, Hout, 1, out_mode == 1);
+  Op op; op.kind = OP_CONV; op.in = src; op.out = out; op.res = res; op.conv = conv; op.stride = stride; op.relu = relu;
+  op.out_mode = out_mode; op.ext = ext;
+  net->ops.push_back(op);
+  return out;
+}
+
+void build_program(yb_net* net) {
+  const yb_net_config& cfg = net->cfg;
+  const int S = cfg.img_size;
+  net->H1 = (S - 1) / 2 + 1;
+  net->H2 = (net->H1 - 1) / 2 + 1;
+  // stem (direct kernel; parameters registered by hand)
+  net->add_param("backbone.conv1.weight", 64 * 3 * 7 * 7);
+  for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) net->add_param(std::string("backbone.bn1") + s, 64);
+  const int stem = new_act(net, 64, net->H1);
+  { Op o; o.kind = OP_STEM; o.out = stem; net->ops.push_back(o); }
+  int x = new_act(net, 64, net->H2);
+  { Op o; o.kind = OP_POOL; o.in = stem; o.out = x; net->ops.push_back(o); }
+
+  const int nblk50[4] = {3, 4, 6, 3}, nblk101[4] = {3, 4, 23, 3};
+  const int* nblk = cfg.depth == 50 ? nblk50 : nblk101;
+  int inpl = 64;
+  int couts[4];
+  for (int s = 0; s < 4; ++s) {
+    const int planes = 64 << s;
+    for (int b = 0; b < nblk[s]; ++b) {
+      const int stride = (b == 0 && s > 0) ? 2 : 1;
+      const std::string p = "backbone.layers." + std::to_string(s) + "." + std::to_string(b);
+      const int c1 = new_conv(net, p + ".conv1.weight", "", p + ".bn1", inpl, planes, 1);
+      const int c2 = new_conv(net, p + ".conv2.weight", "", p + ".bn2", planes, planes, 3);
+      const int c3 = new_conv(net, p + ".conv3.weight", "", p + ".bn3", planes, planes * 4, 1);
+      int r = x;
+      int cd = -1;
+      if (b == 0) cd = new_conv(net, p + ".downsample.0.weight", "", p + ".downsample.1", inpl, planes * 4, 1);
+      const int t1 = add_conv(net, x, c1, 1, 1);
+      const int t2 = add_conv(net, t1, c2, stride, 1);
+      if (b == 0) r = add_conv(net, x, cd, stride, 0);
+      x = add_conv(net, t2, c3, 1, 1, r);
+      inpl = planes * 4;
+    }
+    couts[s] = x;
+  }
+  net->taps["c2"] = couts[0]; net->taps["c3"] = couts[1]; net->taps["c4"] = couts[2]; net->taps["c5"] = couts[3];
+
+  // FPN (modules/yolact.py:73-89)
+  const int fin[3] = {512, 1024, 2048};
+  int lat[3], pred[3];
+  for (int i = 0; i < 3; ++i) {
+    const std::string n = "fpn.lat_layers." + std::to_string(i);
+    lat[i] = new_conv(net, n + ".weight", n + ".bias", "", fin[i], 256, 1);
+  }
+  for (int i = 0; i < 3; ++i) {
+    const std::string n = "fpn.pred_layers." + std::to_string(i) + ".0";
+    pred[i] = new_conv(net, n + ".weight", n + ".bias", "", 256, 256, 3);
+  }
+  int down[2];
+  for (int i = 0; i < 2; ++i) {
+    const std::string n = "fpn.downsample_layers." + std::to_string(i) + ".0";
+    down[i] = new_conv(net, n + ".weight", n + ".bias", "", 256, 256, 3);
+  }
+  const int p5_1 = add_conv(net, couts[3], lat[2], 1, 0);
+  const int p4_1 = add_conv(net, couts[2], lat[1], 1, 0);
+  { Op o; o.kind = OP_UPADD; o.in = p5_1; o.out = p4_1; net->ops.push_back(o); }
+  const int p3_1 = add_conv(net, couts[1], lat[0], 1, 0);
+  { Op o; o.kind = OP_UPADD; o.in = p4_1; o.out = p3_1; net->ops.push_back(o); }
+  int lv[5];
+  lv[2] = add_conv(net, p5_1, pred[2], 1, 1);
+  lv[1] = add_conv(net, p4_1, pred[1], 1, 1);
+  lv[0] = add_conv(net, p3_1, pred[0], 1, 1);
+  lv[3] = add_conv(net, lv[2], down[0], 2, 1);
+  lv[4] = add_conv(net, lv[3], down[1], 2, 1);
+  const char* lvn[5] = {"p3", "p4", "p5", "p6", "p7"};
+  for (int i = 0; i < 5; ++i) net->taps[lvn[i]] = lv[i];
+
+  // ProtoNet (modules/yolact.py:34-53)
+  int t = lv[0];
+  for (int i : {0, 2, 4}) {
+    const std::string n = "proto_net.proto1." + std::to_string(i);
+    t = add_conv(net, t, new_conv(net, n + ".weight", n + ".bias", "", 256, 256, 3), 1, 1);
+  }
+  const int up = new_act(net, 256, 2 * net->acts[t].H);
+  { Op o; o.kind = OP_UP2X; o.in = t; o.out = up; net->ops.push_back(o); }
+  t = add_conv(net, up, new_conv(net, "proto_net.proto2.0.weight", "proto_net.proto2.0.bias", "", 256, 256, 3), 1, 1);
+  net->P = net->acts[t].H;
+  add_conv(net, t, new_conv(net, "proto_net.proto2.2.weight", "proto_net.proto2.2.bias", "", 256, cfg.coef_dim, 1), 1, 1, -1, 1, EXT_PROTO);
+
+  // prediction heads, shared weights over 5 levels (modules/yolact.py:12-31,:149-157)
+  const int R = cfg.num_ratios, NC = cfg.num_classes, K = cfg.coef_dim;
+  const int upf = new_conv(net, "prediction_layers.upfeature.0.weight", "prediction_layers.upfeature.0.bias", "", 256, 256, 3);
+  ConvW hc; hc.Cin = 256; hc.k = 3; hc.Cout = R * (NC + 4 + K); hc.Cout_pad = (hc.Cout + 15) / 16 * 16;
+  hc.cat = {"prediction_layers.conf_layer", "prediction_layers.bbox_layer", "prediction_layers.coef_layer.0"};
+  net->add_param("prediction_layers.bbox_layer.weight", (int64_t)R * 4 * 256 * 9);
+  net->add_param("prediction_layers.bbox_layer.bias", R * 4);
+  net->add_param("prediction_layers.conf_layer.weight", (int64_t)R * NC * 256 * 9);
+  net->add_param("prediction_layers.conf_layer.bias", R * NC);
+  net->add_param("prediction_layers.coef_layer.0.weight", (int64_t)R * K * 256 * 9);
+  net->add_param("prediction_layers.coef_layer.0.bias", R * K);
+  net->convs.push_back(hc);
+  const int head = (int)net->convs.size() - 1;
+  int off = 0;
+  for (int l = 0; l < 5; ++l) {
+    const int Hl = net->acts[lv[l]].H;
+    net->level_size[l] = Hl; net->level_off[l] = off;
+    off += Hl * Hl * R;
+    const int f = add_conv(net, lv[l], upf, 1, 1);
+    const int h = add_conv(net, f, head, 1, 0, -1, 1);
+    Op o; o.kind = OP_HEADFIN; o.in = h; o.level = l; net->ops.push_back(o);
+  }
+  net->A = off;
+
+  // anchors (utils/box_utils.py:86-101, modules/yolact.py:111-114): float64, rounded once
+  net->anchors.resize((size_t)net->A * 4);
+  const double ars[3] = {1.0, 0.5, 2.0};
+  size_t q = 0;
+  for (int l = 0; l < 5; ++l) {
+    const int size = net->level_size[l];
+    const double scale = (double)(int)((double)S / 544.0 * (double)(24 << l));
+    for (int j = 0; j < size; ++j)
+      for (int i = 0; i < size; ++i)
+        for (int r = 0; r < R; ++r) {
+          const double ar = sqrt(ars[r % 3]);
+          net->anchors[q++] = (float)((i + 0.5) / size);
+          net->anchors[q++] = (float)((j + 0.5) / size);
+          net->anchors[q++] = (float)(scale * ar / S);
+          net->anchors[q++] = (float)(scale / ar / S);
+        }
+  }
+}
+
+// liveness + slot assignment
+void plan_memory(yb_net* net) {
+  auto& acts = net->acts;
+  for (auto& a : acts) { a.first = 1 << 30; a.last = -1; }
+  for (int i = 0; i < (int)net->ops.size(); ++i) {
+    const Op& o = net->ops[i];
+    for (int t : {o.in, o.out, o.res}) {
+      if (t < 0) continue;
+      acts[t].first = acts[t].first < i ? acts[t].first : i;
+      acts[t].last = acts[t].last > i ? acts[t].last : i;
+    }
+  }
+  for (auto& kv : net->taps) acts[kv.second].last = 1 << 30;     // keep debug taps alive
+  const size_t esz = dtype_size(net->act_dt);
+  for (auto& a : acts) {
+    a.dt = a.dense_f32 ? DT_F32 : net->act_dt;
+    const size_t rows = a.dense_f32 ? (size_t)net->max_batch * a.H * a.H : (size_t)net->max_batch * (a.H + 2) * (a.H + 2) * a.planes;
+    a.bytes = align_up(rows * a.C * (a.dense_f32 ? 4 : esz), 1024);
+  }
+  std::vector<int> slot_free_at;                                   // op index after which the slot is free
+  net->slot_bytes.clear();
+  std::vector<int> order(acts.size());
+  for (size_t i = 0; i < acts.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return acts[x].first < acts[y].first; });
+  for (int ai : order) {
+    ActBuf& a = acts[ai];
+    if (a.last < 0) continue;
+    // best fit: the smallest free slot that is large enough, else the largest free slot (grown)
+    int best = -1;
+    for (size_t s = 0; s < slot_free_at.size(); ++s) {
+      if (slot_free_at[s] >= a.first) continue;
+      if (best < 0) { best = (int)s; continue; }
+      const size_t sb = net->slot_bytes[s], bb = net->slot_bytes[best];
+      const bool s_fits = sb >= a.bytes, b_fits = bb >= a.bytes;
+      if ((s_fits && (!b_fits || sb < bb)) || (!s_fits && !b_fits && sb > bb)) best = (int)s;
+    }
+    if (best < 0) { slot_free_at.push_back(a.last); net->slot_bytes.push_back(a.bytes); a.slot = (int)slot_free_at.size() - 1; }
+    else { a.slot = best; slot_free_at[best] = a.last; if (net->slot_bytes[best] < a.bytes) net->slot_bytes[best] = a.bytes; }
+  }
+}
+
+int upload(const void* host, size_t bytes, void** dev) {
+  YB_CHECK_CUDA(cudaMalloc(dev, bytes));
+  YB_CHECK_CUDA(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+  return YB_OK;
+}
+
+// fold BN (eval) into scale/shift: y = conv(x)*s + t
+void bn_fold(const yb_net* net, const std::string& bn, int C, std::vector<float>& s, std::vector<float>& t) {
+  const auto& g = net->P_(bn + ".weight"); const auto& b = net->P_(bn + ".bias");
+  const auto& m = net->P_(bn + ".running_mean"); const auto& v = net->P_(bn + ".running_var");
+  s.resize(C); t.resize(C);
+  for (int c = 0; c < C; ++c) {
+    const float sc = g[c] / sqrtf(v[c] + 1e-5f);
+    s[c] = sc; t[c] = b[c] - m[c] * sc;
+  }
+}
+
+int pack_conv(yb_net* net, ConvW& c) {
+  const int k2 = c.k * c.k, Ktot = k2 * c.Cin;
+  const int Cout_alloc = (c.Cout_pad + 63) / 64 * 64;
+  std::vector<float> w((size_t)Cout_alloc * Ktot, 0.f), bias(Cout_alloc, 0.f);
+  auto pack_one = [&](const std::vector<float>& src, int cout, int row0, const std::vector<float>* scale) {
+    // src [cout][Cin][k][k] -> w[row0+co][(r*k+s)*Cin + ci]
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < c.Cin; ++ci)
+        for (int t = 0; t < k2; ++t)
+          w[(size_t)(row0 + co) * Ktot + (size_t)t * c.Cin + ci] = src[((size_t)co * c.Cin + ci) * k2 + t] * (scale ? (*scale)[co] : 1.f);
+  };
+  if (c.cat.empty()) {
+    std::vector<float> s, t;
+    if (!c.bnname.empty()) bn_fold(net, c.bnname, c.Cout, s, t);
+    pack_one(net->P_(c.wname), c.Cout, 0, c.bnname.empty() ? nullptr : &s);
+    for (int co = 0; co < c.Cout; ++co) {
+      float b = c.bname.empty() ? 0.f : net->P_(c.bname)[co];
+      bias[co] = c.bnname.empty() ? b : b * s[co] + t[co];
+    }
+  } else {
+    int row = 0;
+    for (const auto& n : c.cat) {
+      const auto& ww = net->P_(n + ".weight"); const auto& bb = net->P_(n + ".bias");
+      const int cout = (int)bb.size();
+      pack_one(ww, cout, row, nullptr);
+      for (int co = 0; co < cout; ++co) bias[row + co] = bb[co];
+      row += cout;
+    }
+  }
+  if (net->act_dt == DT_F32) {
+    YB_PROPAGATE(upload(w.data(), w.size() * 4, &c.d_w));
+  } else {
+    std::vector<__nv_bfloat16> wb(w.size());
+    for (size_t i = 0; i < w.size(); ++i) wb[i] = __float2bfloat16_rn(w[i]);
+    YB_PROPAGATE(upload(wb.data(), wb.size() * 2, &c.d_w));
+  }
+  YB_PROPAGATE(upload(bias.data(), bias.size() * 4, (void**)&c.d_b));
+  return YB_OK;
+}
+
+void* act_ptr(const yb_net* net, int a) { return net->slots[net->acts[a].slot]; }
+
+// fill ConvArgs for op at batch B
+void conv_args(const yb_net* net, const Op& o, int B, ConvArgs* a, void* ext_out) {
+  const ConvW& c = net->convs[o.conv];
+  const ActBuf& in = net->acts[o.in];
+  memset(a, 0, sizeof(*a));
+  a->in = act_ptr(net, o.in);
+  a->weight = c.d_w; a->bias = c.d_b;
+  a->residual = o.res >= 0 ? act_ptr(net, o.res) : nullptr;
+  a->out = o.ext != EXT_NONE ? ext_out : act_ptr(net, o.out);
+  a->act_dt = net->act_dt; a->B = B;
+  a->g.H = in.H; a->g.W = in.H;
+  a->Cin = c.Cin; a->Cout = c.Cout; a->Cout_pad = c.Cout_pad;
+  a->relu = o.relu; a->out_mode = o.out_mode;
+  const int Wp = in.H + 2;
+  const long long plane_rows = (long long)net->max_batch * Wp * Wp;      // parity planes sit at max-batch strides
+  a->in_rows = plane_rows * in.planes;
+  if (o.stride == 1) {
+    a->ntaps = c.k * c.k;
+    for (int r = 0; r < c.k; ++r)
+      for (int s = 0; s < c.k; ++s) a->tap_shift[r * c.k + s] = c.k == 1 ? 0 : (r - 1) * Wp + (s - 1);
+    a->in_rows = (long long)B * Wp * Wp;
+  } else if (c.k == 1) {
+    a->ntaps = 1; a->tap_shift[0] = 0;
+  } else {
+    a->ntaps = 9;
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) {
+        const int pr = r == 1 ? 0 : 1, ps = s == 1 ? 0 : 1, dy = r == 0 ? -1 : 0, dx = s == 0 ? -1 : 0;
+        a->tap_shift[r * 3 + s] = (int)((pr * 2 + ps) * plane_rows) + dy * Wp + dx;
+      }
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int yb_net_create(const yb_net_config* cfg, yb_net** out) {
+  YB_REQUIRE(cfg && out, YB_ERR_INVALID, "yb_net_create: NULL argument");
+  YB_REQUIRE(cfg->depth == 50 || cfg->depth == 101, YB_ERR_UNSUPPORTED, "yb_net_create: depth=%d (50 or 101)", cfg->depth);
+  YB_REQUIRE(cfg->img_size >= 64 && cfg->img_size <= 4096, YB_ERR_INVALID, "yb_net_create: img_size=%d", cfg->img_size);
+  YB_REQUIRE(cfg->num_classes >= 2 && cfg->num_ratios >= 1 && cfg->num_ratios <= 3, YB_ERR_INVALID, "yb_net_create: num_classes=%d num_ratios=%d", cfg->num_classes, cfg->num_ratios);
+  YB_REQUIRE(cfg->coef_dim > 0 && cfg->coef_dim % 4 == 0 && cfg->coef_dim <= 64, YB_ERR_UNSUPPORTED, "yb_net_create: coef_dim=%d", cfg->coef_dim);
+  yb_net* net = new yb_net();
+  net->cfg = *cfg;
+  build_program(net);
+  *out = net;
+  return YB_OK;
+}
+
+extern "C" void yb_net_destroy(yb_net* net) {
+  if (!net) return;
+  for (void* p : net->slots) cudaFree(p);
+  for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); }
+  for (auto& o : net->ops) tc_plan_destroy(o.tc);
+  for (void* p : {(void*)net->d_anchors, (void*)net->d_stem_w, (void*)net->d_stem_b, (void*)net->d_img, (void*)net->d_cls,
+                  (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws, (void*)net->d_cnt, (void*)net->d_ocls,
+                  (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
+    cudaFree(p);
+  if (net->own_stream) cudaStreamDestroy(net->own_stream);
+  delete net;
+}
+
+extern "C" int yb_net_num_params(const yb_net* net) { return net ? (int)net->params.size() : 0; }
+
+extern "C" int yb_net_param_info(const yb_net* net, int i, const char** name, int64_t* count) {
+  YB_REQUIRE(net && i >= 0 && i < (int)net->params.size(), YB_ERR_INVALID, "yb_net_param_info: index %d", i);
+  if (name) *name = net->params[i].name.c_str();
+  if (count) *count = net->params[i].count;
+  return YB_OK;
+}
+
+extern "C" int yb_net_set_param(yb_net* net, const char* name, const float* data, int64_t count) {
+  YB_REQUIRE(net && name && data, YB_ERR_INVALID, "yb_net_set_param: NULL argument");
+  auto it = net->pidx.find(name);
+  YB_REQUIRE(it != net->pidx.end(), YB_ERR_INVALID, "yb_net_set_param: unexpected parameter '%s'", name);
+  Param& p = net->params[it->second];
+  YB_REQUIRE(p.count == count, YB_ERR_INVALID, "yb_net_set_param: '%s' has %lld elements, expected %lld", name, (long long)count, (long long)p.count);
+  p.data.assign(data, data + count);
+  p.set = true;
+  net->finalized = false;
+  return YB_OK;
+}
+
+extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
+  YB_REQUIRE(net, YB_ERR_INVALID, "yb_net_finalize: NULL net");
+  YB_REQUIRE(max_batch >= 1 && max_batch <= 4096, YB_ERR_INVALID, "yb_net_finalize: max_batch=%d", max_batch);
+  YB_REQUIRE(precision == YB_PREC_FP32 || precision == YB_PREC_BF16, YB_ERR_INVALID, "yb_net_finalize: precision=%d", precision);
+  for (const auto& p : net->params)
+    YB_REQUIRE(p.set, YB_ERR_STATE, "yb_net_finalize: parameter '%s' was never set (strict load)", p.name.c_str());
+  int cc_major = 0;
+  YB_PROPAGATE(yb_device_info(nullptr, &cc_major, nullptr));
+  YB_REQUIRE(cc_major == 10, YB_ERR_UNSUPPORTED, "yb_net_finalize: this library is built for sm_100a only (device cc major %d)", cc_major);
+  // release a previous finalisation
+  for (void* p : net->slots) cudaFree(p);
+  net->slots.clear();
+  for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); c.d_w = nullptr; c.d_b = nullptr; }
+  for (auto& o : net->ops) { tc_plan_destroy(o.tc); o.tc = nullptr; }
+  cudaFree(net->d_anchors); cudaFree(net->d_stem_w); cudaFree(net->d_stem_b);
+  net->d_anchors = net->d_stem_w = net->d_stem_b = nullptr;
+
+  net->max_batch = max_batch; net->precision = precision;
+  net->act_dt = precision == YB_PREC_BF16 ? DT_BF16 : DT_F32;
+  plan_memory(net);
+  net->slots.resize(net->slot_bytes.size(), nullptr);
+  for (size_t s = 0; s < net->slot_bytes.size(); ++s) {
+    YB_CHECK_CUDA(cudaMalloc(&net->slots[s], net->slot_bytes[s]));
+    YB_CHECK_CUDA(cudaMemset(net->slots[s], 0, net->slot_bytes[s]));
+  }
+  for (auto& c : net->convs) YB_PROPAGATE(pack_conv(net, c));
+  {  // stem: [64][3][7][7] * bn scale -> [7][7][3][64]
+    std::vector<float> s, t, w(147 * 64);
+    bn_fold(net, "backbone.bn1", 64, s, t);
+    const auto& src = net->P_("backbone.conv1.weight");
+    for (int co = 0; co < 64; ++co)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int r = 0; r < 7; ++r)
+          for (int q = 0; q < 7; ++q) w[((r * 7 + q) * 3 + ci) * 64 + co] = src[((co * 3 + ci) * 7 + r) * 7 + q] * s[co];
+    YB_PROPAGATE(upload(w.data(), w.size() * 4, (void**)&net->d_stem_w));
+    YB_PROPAGATE(upload(t.data(), t.size() * 4, (void**)&net->d_stem_b));
+  }
+  YB_PROPAGATE(upload(net->anchors.data(), net->anchors.size() * 4, (void**)&net->d_anchors));
+  // tensor-core plans (bf16 only)
+  if (net->act_dt == DT_BF16) {
+    for (auto& o : net->ops) {
+      if (o.kind != OP_CONV) continue;
+      ConvArgs a;
+      static float dummy;
+      conv_args(net, o, max_batch, &a, &dummy);
+      if (tc_supported(a)) YB_PROPAGATE(tc_plan_create(a, max_batch, &o.tc));
+    }
+  }
+  net->finalized = true;
+  return YB_OK;
+}
+
+extern "C" int yb_net_num_anchors(const yb_net* net) { return net ? net->A : 0; }
+extern "C" int yb_net_proto_size(const yb_net* net) { return net ? net->P : 0; }
+extern "C" const float* yb_net_anchors_device(const yb_net* net) { return net ? net->d_anchors : nullptr; }
+extern "C" int yb_net_anchors_host(const yb_net* net, float* out) {
+  YB_REQUIRE(net && out, YB_ERR_INVALID, "yb_net_anchors_host: NULL argument");
+  memcpy(out, net->anchors.data(), net->anchors.size() * 4);
+  return YB_OK;
+}
+
+extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* cls, float* box, float* coef, float* proto,
+                              void* stream_) {
+  YB_REQUIRE(net && img && cls && box && coef && proto, YB_ERR_INVALID, "yb_net_forward: NULL argument");
+  YB_REQUIRE(net->finalized, YB_ERR_STATE, "yb_net_forward: call yb_net_finalize first");
+  YB_REQUIRE(batch >= 1 && batch <= net->max_batch, YB_ERR_INVALID, "yb_net_forward: batch=%d outside [1,%d]", batch, net->max_batch);
+  cudaStream_t s = (cudaStream_t)stream_;
+  const yb_net_config& cfg = net->cfg;
+  for (const Op& o : net->ops) {
+    switch (o.kind) {
+      case OP_STEM:
+        YB_PROPAGATE(launch_stem(img, net->d_stem_w, net->d_stem_b, act_ptr(net, o.out), net->act_dt, batch, cfg.img_size, net->H1, s));
+        break;
+      case OP_POOL:
+        YB_PROPAGATE(launch_maxpool(act_ptr(net, o.in), act_ptr(net, o.out), net->act_dt, batch, 64, net->H1, net->H2, s));
+        break;
+      case OP_SPLIT: {
+        const ActBuf& out = net->acts[o.out];
+        const long long plane_rows = (long long)net->max_batch * (out.H + 2) * (out.H + 2);
+        YB_PROPAGATE(launch_phase_split(act_ptr(net, o.in), act_ptr(net, o.out), net->act_dt, batch, out.C, net->acts[o.in].H, out.H,
+                                        out.planes, plane_rows, s));
+        break;
+      }
+      case OP_CONV: {
+        ConvArgs a;
+        conv_args(net, o, batch, &a, proto);
+        if (o.tc) YB_PROPAGATE(launch_conv_tc(o.tc, a, s));
+        else YB_PROPAGATE(launch_conv_simt(a, s));
+        break;
+      }
+      case OP_UPADD:
+        YB_PROPAGATE(launch_upsample_add(act_ptr(net, o.in), act_ptr(net, o.out), net->act_dt, batch, 256, net->acts[o.in].H,
+                                         net->acts[o.out].H, s));
+        break;
+      case OP_UP2X:
+        YB_PROPAGATE(launch_upsample2x_ac(act_ptr(net, o.in), act_ptr(net, o.out), net->act_dt, batch, 256, net->acts[o.in].H, s));
+        break;
+      case OP_HEADFIN: {
+        const ActBuf& h = net->acts[o.in];
+        YB_PROPAGATE(launch_head_finalize((const float*)act_ptr(net, o.in), h.C, batch, h.H * h.H, cfg.num_ratios, cfg.num_classes,
+                                          cfg.coef_dim, net->level_off[o.level], net->A, cls, box, coef, s));
+        break;
+      }
+    }
+  }
+  return YB_OK;
+}
+
+extern "C" int yb_net_read_activation(yb_net* net, const char* name, int batch, float* out, int64_t out_count, int* C, int* H,
+                                      int* W, void* stream) {
+  YB_REQUIRE(net && name, YB_ERR_INVALID, "yb_net_read_activation: NULL argument");
+  YB_REQUIRE(net->finalized, YB_ERR_STATE, "yb_net_read_activation: net not finalized");
+  auto it = net->taps.find(name);
+  YB_REQUIRE(it != net->taps.end(), YB_ERR_INVALID, "yb_net_read_activation: unknown tap '%s'", name);
+  const ActBuf& a = net->acts[it->second];
+  if (C) *C = a.C;
+  if (H) *H = a.H;
+  if (W) *W = a.H;
+  if (!out) return YB_OK;
+  YB_REQUIRE(out_count >= (int64_t)batch * a.C * a.H * a.H, YB_ERR_INVALID, "yb_net_read_activation: output too small");
+  return launch_read_activation(act_ptr(net, it->second), a.dt, batch, a.C, a.H, out, (cudaStream_t)stream);
+}
+
+extern "C" const float* yb_net_last_proto(const yb_net* net) { return net ? net->d_proto : nullptr; }
+
+extern "C" int yb_net_detect_host(yb_net* net, const float* img_host, int batch, const yb_detect_params* p,
+                                  int32_t* out_count, int32_t* out_class, int32_t* out_anchor, float* out_score,
+                                  float* out_box, float* out_coef) {
+  YB_REQUIRE(net && img_host && p && out_count && out_class && out_anchor && out_score && out_box, YB_ERR_INVALID,
+             "yb_net_detect_host: NULL argument");
+  YB_REQUIRE(net->finalized, YB_ERR_STATE, "yb_net_detect_host: call yb_net_finalize first");
+  YB_REQUIRE(batch >= 1 && batch <= net->max_batch, YB_ERR_INVALID, "yb_net_detect_host: batch=%d outside [1,%d]", batch, net->max_batch);
+  YB_REQUIRE(p->num_classes == net->cfg.num_classes && p->coef_dim == net->cfg.coef_dim, YB_ERR_INVALID,
+             "yb_net_detect_host: params do not match the network (classes %d/%d, coef %d/%d)", p->num_classes,
+             net->cfg.num_classes, p->coef_dim, net->cfg.coef_dim);
+  const size_t B = net->max_batch, A = net->A, C = net->cfg.num_classes, K = net->cfg.coef_dim, S = net->cfg.img_size, P = net->P;
+  const size_t D = p->max_det;
+  if (!net->own_stream) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&net->own_stream, cudaStreamNonBlocking));
+  if (net->host_batch != (int)B || net->host_maxdet < (int)D) {
+    for (void* q : {(void*)net->d_img, (void*)net->d_cls, (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws,
+                    (void*)net->d_cnt, (void*)net->d_ocls, (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
+      cudaFree(q);
+    YB_CHECK_CUDA(cudaMalloc(&net->d_img, B * 3 * S * S * 4));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_cls, B * A * C * 4));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_box, B * A * 16));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_coef, B * A * K * 4));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_proto, B * P * P * K * 4));
+    yb_detect_params pm = *p;
+    pm.top_k = 256; pm.max_det = 256;
+    net->ws_bytes = yb_detect_workspace_bytes((int)B, (int)A, &pm);
+    YB_CHECK_CUDA(cudaMalloc(&net->d_ws, net->ws_bytes));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_cnt, B * 4));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_ocls, B * 256 * 4));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_oanc, B * 256 * 4));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_osc, B * 256 * 4));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_obox, B * 256 * 16));
+    YB_CHECK_CUDA(cudaMalloc(&net->d_ocoef, B * 256 * K * 4));
+    net->host_batch = (int)B; net->host_maxdet = 256;
+  }
+  cudaStream_t s = net->own_stream;
+  const size_t b = batch;
+  YB_CHECK_CUDA(cudaMemcpyAsync(net->d_img, img_host, b * 3 * S * S * 4, cudaMemcpyHostToDevice, s));
+  YB_PROPAGATE(yb_net_forward(net, net->d_img, batch, net->d_cls, net->d_box, net->d_coef, net->d_proto, s));
+  YB_PROPAGATE(yb_detect(net->d_cls, net->d_box, net->d_coef, net->d_anchors, batch, (int)A, p, net->d_ws, net->ws_bytes, net->d_cnt,
+                         net->d_ocls, net->d_oanc, net->d_osc, net->d_obox, out_coef ? net->d_ocoef : nullptr, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(out_count, net->d_cnt, b * 4, cudaMemcpyDeviceToHost, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(out_class, net->d_ocls, b * D * 4, cudaMemcpyDeviceToHost, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(out_anchor, net->d_oanc, b * D * 4, cudaMemcpyDeviceToHost, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(out_score, net->d_osc, b * D * 4, cudaMemcpyDeviceToHost, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(out_box, net->d_obox, b * D * 16, cudaMemcpyDeviceToHost, s));
+  if (out_coef) YB_CHECK_CUDA(cudaMemcpyAsync(out_coef, net->d_ocoef, b * D * K * 4, cudaMemcpyDeviceToHost, s));
+  YB_CHECK_CUDA(cudaStreamSynchronize(s));
+  return YB_OK;
+}
