@@ -118,7 +118,10 @@ YB_API int yb_mask_assemble(const float* proto, const float* coef, const float* 
  * ---------------------------------------------------------------------------------------- */
 typedef struct yb_net yb_net;
 
-typedef enum { YB_PREC_FP32 = 0, YB_PREC_BF16 = 1 } yb_precision;
+/* FP32: CUDA-core fp32 (parity mode).  BF16 / FP16: 16-bit activations and weights on the
+ * tcgen05 tensor cores with fp32 accumulation (FP16 has TF32's 10-bit mantissa: the accuracy
+ * of the reference's own GPU path; BF16 has 8 bits). */
+typedef enum { YB_PREC_FP32 = 0, YB_PREC_BF16 = 1, YB_PREC_FP16 = 2 } yb_precision;
 
 typedef struct {
   int depth;          /* 50 or 101 */
@@ -152,6 +155,15 @@ YB_API int yb_net_forward(yb_net* net, const float* img, int batch,
  * last forward into out as NCHW float32 [B,C,H,W] (device). */
 YB_API int yb_net_read_activation(yb_net* net, const char* name, int batch, float* out, int64_t out_count,
                            int* C, int* H, int* W, void* stream);
+
+/* One convolution layer of the engine as a standalone op (unit tests / per-layer parity at the
+ * shapes of SURVEY.md App. A): y = [relu]( conv2d(x, w, stride, pad=k/2) + bias [+ residual] ).
+ * x [B,Cin,H,H] and residual/out [B,Cout,Ho,Ho] are NCHW float32 on the DEVICE; w [Cout,Cin,k,k]
+ * and bias [Cout] on the HOST.  k in {1,3}, stride in {1,2}, Cin % 64 == 0.  precision as in
+ * yb_precision; use_tc = 1 selects the tcgen05 kernel (16-bit precisions only), 0 the CUDA-core
+ * kernel.  Synchronous (allocates scratch internally). */
+YB_API int yb_conv2d(const float* x, int batch, int cin, int h, const float* w, const float* bias, int cout, int k,
+                     int stride, int relu, const float* residual, int precision, int use_tc, float* out);
 
 /* End-to-end with HOST buffers: H2D(img) -> forward -> detect -> D2H(detections).
  * img_host [B,3,S,S]; outputs as in yb_detect (host).  The proto/coef needed for masks stay on

@@ -54,6 +54,7 @@ PROTOTYPES = {
     'yb_net_forward': (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     'yb_net_read_activation': (C.c_int, [vp, C.c_char_p, C.c_int, vp, C.c_int64, C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), vp]),
+    'yb_conv2d': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp]),
     'yb_net_detect_host': (C.c_int, [vp, vp, C.c_int, C.POINTER(DetectParams), vp, vp, vp, vp, vp, vp]),
     'yb_net_last_proto': (vp, [vp]),
 }

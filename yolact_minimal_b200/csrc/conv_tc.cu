@@ -1,9 +1,422 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the tensor-core path lands).
+// tcgen05 implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+//   out[M, Cout] = epilogue( sum_{tap} A[M + shift_tap, Cin] * W_tap[Cin, Cout] )
+//
+// on the haloed NHWC layout of layers.cuh, where every convolution tap is a constant row shift
+// of the activation matrix.  Persistent, warp-specialised CTA (192 threads, 1 CTA / SM):
+//   warp 0      TMA producer: per k-block one 128x64 A tile (row coordinate m0 + shift_tap,
+//               out-of-range rows zero-filled by TMA = the conv padding) and one BNx64 weight
+//               tile, both 128B-swizzled, into a ring of shared-memory stages (mbarrier full/empty)
+//   warp 1      allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16) from one elected lane,
+//               tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2..5  epilogue: tcgen05.ld the 128xBN fp32 accumulator (double-buffered in TMEM so the
+//               next tile's MMAs overlap), + folded-BN bias, + residual, ReLU, halo zeroing,
+//               bf16 (or dense fp32) stores
+// Tiles are scheduled round-robin over the persistent grid, N-tiles of one M-tile adjacent so
+// the A tile is shared through L2.
 #include "layers.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <mutex>
+
 namespace yb {
-struct TcPlan {};
-bool tc_supported(const ConvArgs&) { return false; }
-int tc_plan_create(const ConvArgs&, int, TcPlan**) { set_error("tc path not built"); return YB_ERR_UNSUPPORTED; }
-void tc_plan_destroy(TcPlan*) {}
-int launch_conv_tc(const TcPlan*, const ConvArgs&, cudaStream_t) { set_error("tc path not built"); return YB_ERR_UNSUPPORTED; }
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_STAGE = TC_BM * TC_BK * 2;   // 16 KiB
+
+struct TcParams {
+  long long M;            // rows to produce (B * plane)
+  int m_tiles, n_tiles;
+  int kb_per_tap;         // Cin / 64
+  int ntaps;
+  int tap_shift[kMaxTaps];
+  int BN;                 // N tile (multiple of 16, <= 256)
+  int tmem_cols;          // allocated columns (power of two >= 2*BN)
+  int stages;
+  int Cout, Cout_pad, relu, out_mode;
+  int is_f16;             // operands fp16 (else bf16)
+  Geom g;
+  const float* bias;
+  const void* residual;
+  void* out;
+};
+
+struct TcPlan {
+  CUtensorMap tmA, tmB;
+  int BN, stages, tmem_cols;
+  size_t smem_bytes;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <bool F16> __device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (F16) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+template <bool F16> __device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+
+// epilogue for `n` (16 or 32) consecutive columns starting at global column col of row m
+template <int NCOL, bool F16>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t* acc, long long m, int col, bool valid, bool halo,
+                                               int img, int y, int x) {
+  float v[NCOL];
+#pragma unroll
+  for (int i = 0; i < NCOL; i += 4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+    v[i] = __uint_as_float(acc[i]) + b.x; v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
+    v[i + 2] = __uint_as_float(acc[i + 2]) + b.z; v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+  }
+  if (!valid) return;
+  if (p.out_mode == 0) {
+    uint16_t* o = (uint16_t*)p.out + m * p.Cout + col;
+    if (halo) {
+#pragma unroll
+      for (int i = 0; i < NCOL; i += 8) *reinterpret_cast<uint4*>(o + i) = make_uint4(0, 0, 0, 0);
+      return;
+    }
+    if (p.residual) {
+      const uint16_t* r = (const uint16_t*)p.residual + m * p.Cout + col;
+#pragma unroll
+      for (int i = 0; i < NCOL; i += 8) {
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r + i));
+        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack2<F16>(rw[j]);
+          v[i + 2 * j] += f.x; v[i + 2 * j + 1] += f.y;
+        }
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < NCOL; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NCOL; i += 8) {
+      uint4 pk;
+      pk.x = pack2<F16>(v[i], v[i + 1]); pk.y = pack2<F16>(v[i + 2], v[i + 3]);
+      pk.z = pack2<F16>(v[i + 4], v[i + 5]); pk.w = pack2<F16>(v[i + 6], v[i + 7]);
+      *reinterpret_cast<uint4*>(o + i) = pk;
+    }
+  } else if (!halo) {
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < NCOL; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    const long long r = ((long long)img * p.g.H + (y - 1)) * p.g.W + (x - 1);
+    float* o = (float*)p.out + r * p.Cout_pad + col;
+#pragma unroll
+    for (int i = 0; i < NCOL; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024B alignment
+  const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_stage);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int num_kb = p.ntaps * p.kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int m0 = m_tile * TC_BM, n0 = n_tile * p.BN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int row = m0 + p.tap_shift[t];
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], TC_A_STAGE + b_stage);
+            tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmA, kb * TC_BK, row, &full[stage]);
+            tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0, &full[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16 (1) or f16 (0), K-major both, N=BN, M=128
+      const uint32_t fmt = p.is_f16 ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
+          const uint64_t db = umma_desc(smem_u32(sB + (size_t)stage * b_stage));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                   // smem stage free once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                   // accumulator complete
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const long long m = (long long)m_tile * TC_BM + row_in_tile;
+      const bool valid = m < p.M;
+      int img = 0, y = 0, x = 0;
+      bool halo = false;
+      if (valid) {
+        const int plane = p.g.plane();
+        img = (int)(m / plane);
+        const int pos = (int)(m - (long long)img * plane);
+        y = pos / p.g.Wp(); x = pos - y * p.g.Wp();
+        halo = y == 0 || y == p.g.H + 1 || x == 0 || x == p.g.W + 1;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
+      const int n0 = n_tile * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        if (c0 + 32 <= p.BN) {
+          tmem_ld32(t_base + c0, r);
+          tmem_ld_wait();
+          if (p.is_f16) epilogue_chunk<32, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
+          else epilogue_chunk<32, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
+        } else {
+          tmem_ld16(t_base + c0, r);
+          tmem_ld_wait();
+          if (p.is_f16) epilogue_chunk<16, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
+          else epilogue_chunk<16, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows, bool f16) {
+  EncodeTiledFn enc = get_encode();
+  YB_REQUIRE(enc != nullptr, YB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {inner, rows};
+  const cuuint64_t strides[1] = {inner * 2};
+  const cuuint32_t box[2] = {TC_BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YB_REQUIRE(r == CUDA_SUCCESS, YB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu box_rows=%u", (int)r,
+             (unsigned long long)inner, (unsigned long long)rows, box_rows);
+  return YB_OK;
+}
+
+static int pick_bn(int cout_pad) {
+  if (cout_pad % 256 == 0) return 256;
+  if (cout_pad <= 256 && cout_pad % 16 == 0) return cout_pad;          // 32, 64, 128, ...
+  if (cout_pad % 2 == 0 && (cout_pad / 2) % 16 == 0 && cout_pad / 2 <= 256) return cout_pad / 2;   // 352 -> 176
+  return 0;
+}
+
+bool tc_supported(const ConvArgs& a) {
+  if (a.act_dt != DT_BF16 && a.act_dt != DT_F16) return false;
+  if (a.Cin % TC_BK != 0) return false;
+  if (a.out_mode == 0 && a.Cout != a.Cout_pad) return false;
+  return pick_bn(a.Cout_pad) != 0;
+}
+
+int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
+  (void)max_batch;
+  YB_REQUIRE(tc_supported(a), YB_ERR_UNSUPPORTED, "tc_plan_create: unsupported conv Cin=%d Cout_pad=%d", a.Cin, a.Cout_pad);
+  TcPlan* pl = new TcPlan();
+  pl->BN = pick_bn(a.Cout_pad);
+  int cols = 32;
+  while (cols < 2 * pl->BN) cols <<= 1;
+  pl->tmem_cols = cols;
+  const size_t per_stage = TC_A_STAGE + (size_t)pl->BN * TC_BK * 2;
+  int stages = (int)((200 * 1024) / per_stage);
+  if (stages > 8) stages = 8;
+  pl->stages = stages;
+  pl->smem_bytes = (size_t)stages * per_stage + 1024 /*align*/ + 256 /*barriers*/;
+  const int Ktot = a.ntaps * a.Cin;
+  const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
+  const bool f16 = a.act_dt == DT_F16;
+  int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, TC_BM, f16);
+  if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)pl->BN, f16);
+  if (s != YB_OK) { delete pl; return s; }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  if (attr_err != cudaSuccess) { delete pl; set_error("cudaFuncSetAttribute(k_conv_tc) failed: %s", cudaGetErrorString(attr_err)); return YB_ERR_CUDA; }
+  *out = pl;
+  return YB_OK;
+}
+
+void tc_plan_destroy(TcPlan* p) { delete p; }
+
+int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
+  TcParams p;
+  p.M = (long long)a.B * a.g.plane();
+  p.m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
+  p.n_tiles = a.Cout_pad / pl->BN;
+  p.kb_per_tap = a.Cin / TC_BK;
+  p.ntaps = a.ntaps;
+  for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
+  p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
+  p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
+  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sms ? total : sms;
+  k_conv_tc<<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, p);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
 }  // namespace yb

@@ -13,6 +13,10 @@ template <> struct Act<float> {
   static __device__ __forceinline__ float ld(const float* p) { return *p; }
   static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
 };
+template <> struct Act<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+};
 template <> struct Act<__nv_bfloat16> {
   static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
@@ -110,8 +114,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   const long long M = (long long)a.B * a.g.plane();
   dim3 grid((unsigned)((M + SBM - 1) / SBM), (unsigned)ceil_div(a.Cout_pad, SBN));
   YB_REQUIRE(a.Cin % SBK == 0, YB_ERR_UNSUPPORTED, "conv_simt: Cin=%d not a multiple of %d", a.Cin, SBK);
-  if (a.act_dt == DT_F32) k_conv_simt<float><<<grid, 256, 0, s>>>(a, M);
-  else k_conv_simt<__nv_bfloat16><<<grid, 256, 0, s>>>(a, M);
+  YB_DISPATCH_DT(a.act_dt, (k_conv_simt<T><<<grid, 256, 0, s>>>(a, M)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -183,7 +186,7 @@ __global__ void k_zero_halo(T* __restrict__ t, int B, int C, int H) {
     else if (e < 2 * Hp) { y = Hp - 1; x = e - Hp; }
     else if (e < 3 * Hp - 2) { y = e - 2 * Hp + 1; x = 0; }
     else { y = e - (3 * Hp - 2) + 1; x = Hp - 1; }
-    t[(((size_t)b * Hp + y) * Hp + x) * C + c] = T(0.f);
+    Act<T>::st(t + (((size_t)b * Hp + y) * Hp + x) * C + c, 0.f);
   }
 }
 
@@ -191,17 +194,12 @@ int launch_stem(const float* img, const float* w, const float* bias, void* out, 
                 cudaStream_t s) {
   const size_t smem = (147 * 64 + 3 * SP * (SP + 1)) * sizeof(float);
   dim3 grid(ceil_div(H1, ST), ceil_div(H1, ST), B);
-  if (out_dt == DT_F32) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(k_stem<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stem<float><<<grid, 256, smem, s>>>(img, w, bias, (float*)out, S, H1);
-    YB_CHECK_LAUNCH();
-    k_zero_halo<float><<<148, 256, 0, s>>>((float*)out, B, 64, H1);
-  } else {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(k_stem<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stem<__nv_bfloat16><<<grid, 256, smem, s>>>(img, w, bias, (__nv_bfloat16*)out, S, H1);
-    YB_CHECK_LAUNCH();
-    k_zero_halo<__nv_bfloat16><<<148, 256, 0, s>>>((__nv_bfloat16*)out, B, 64, H1);
-  }
+  cudaError_t attr = cudaSuccess;
+  YB_DISPATCH_DT(out_dt, attr = cudaFuncSetAttribute(k_stem<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                 if (attr == cudaSuccess) k_stem<T><<<grid, 256, smem, s>>>(img, w, bias, (T*)out, S, H1));
+  YB_CHECK_CUDA(attr);
+  YB_CHECK_LAUNCH();
+  YB_DISPATCH_DT(out_dt, (k_zero_halo<T><<<148, 256, 0, s>>>((T*)out, B, 64, H1)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -237,8 +235,7 @@ __global__ void k_maxpool(const T* __restrict__ in, T* __restrict__ out, int B, 
 int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s) {
   const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  if (dt == DT_F32) k_maxpool<float><<<blocks, 256, 0, s>>>((const float*)in, (float*)out, B, C, Hin, Hout);
-  else k_maxpool<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, C, Hin, Hout);
+  YB_DISPATCH_DT(dt, (k_maxpool<T><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -272,8 +269,7 @@ int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin,
                        long long plane_stride_rows, cudaStream_t s) {
   const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C * nplanes;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  if (dt == DT_F32) k_phase_split<float><<<blocks, 256, 0, s>>>((const float*)in, (float*)out, B, C, Hin, Hout, nplanes, plane_stride_rows);
-  else k_phase_split<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, C, Hin, Hout, nplanes, plane_stride_rows);
+  YB_DISPATCH_DT(dt, (k_phase_split<T><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, nplanes, plane_stride_rows)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -317,8 +313,7 @@ int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, in
   const long long total = (long long)B * (Hf + 2) * (Hf + 2) * C;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
   const float scale = (float)Hc / (float)Hf;
-  if (dt == DT_F32) k_bilinear<float, true, false><<<blocks, 256, 0, s>>>((const float*)coarse, (float*)fine, B, C, Hc, Hf, scale);
-  else k_bilinear<__nv_bfloat16, true, false><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)coarse, (__nv_bfloat16*)fine, B, C, Hc, Hf, scale);
+  YB_DISPATCH_DT(dt, (k_bilinear<T, true, false><<<blocks, 256, 0, s>>>((const T*)coarse, (T*)fine, B, C, Hc, Hf, scale)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -329,8 +324,7 @@ int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hi
   const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
   const float scale = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
-  if (dt == DT_F32) k_bilinear<float, false, true><<<blocks, 256, 0, s>>>((const float*)in, (float*)out, B, C, Hin, Hout, scale);
-  else k_bilinear<__nv_bfloat16, false, true><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, C, Hin, Hout, scale);
+  YB_DISPATCH_DT(dt, (k_bilinear<T, false, true><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, scale)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -397,11 +391,34 @@ __global__ void k_read_act(const T* __restrict__ in, int B, int C, int H, float*
   }
 }
 
+template <typename T>
+__global__ void k_write_act(const float* __restrict__ in, int B, int C, int H, T* __restrict__ out) {
+  const int Hp = H + 2;
+  const long long total = (long long)B * Hp * Hp * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int xp = (int)(r % Hp); r /= Hp;
+    const int yp = (int)(r % Hp);
+    const int b = (int)(r / Hp);
+    float v = 0.f;
+    if (yp >= 1 && yp <= H && xp >= 1 && xp <= H) v = in[(((size_t)b * C + c) * H + yp - 1) * H + xp - 1];
+    Act<T>::st(out + i, v);
+  }
+}
+
+int launch_write_activation(const float* in_nchw, int dt, int B, int C, int H, void* out, cudaStream_t s) {
+  const long long total = (long long)B * C * (H + 2) * (H + 2);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  YB_DISPATCH_DT(dt, (k_write_act<T><<<blocks, 256, 0, s>>>(in_nchw, B, C, H, (T*)out)));
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
 int launch_read_activation(const void* in, int dt, int B, int C, int H, float* out, cudaStream_t s) {
   const long long total = (long long)B * C * H * H;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  if (dt == DT_F32) k_read_act<float><<<blocks, 256, 0, s>>>((const float*)in, B, C, H, out);
-  else k_read_act<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, B, C, H, out);
+  YB_DISPATCH_DT(dt, (k_read_act<T><<<blocks, 256, 0, s>>>((const T*)in, B, C, H, out)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }

@@ -11,10 +11,11 @@
 // Every producer writes zeros into the halo rows/columns of its output.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace yb {
 
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 static inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 
 struct Geom {          // geometry of a haloed tensor
@@ -43,9 +44,17 @@ struct ConvArgs {
   long long in_rows;     // total rows addressable in `in` (for bounds checks)
 };
 
+// run `expr` with type alias T bound to the C++ type of DType dt
+#define YB_DISPATCH_DT(dt, ...)                                   \
+  do {                                                            \
+    if ((dt) == DT_F32) { using T = float; __VA_ARGS__; }         \
+    else if ((dt) == DT_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = __half; __VA_ARGS__; }                       \
+  } while (0)
+
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 
-// conv_tc.cu: tcgen05 path (bf16 only).  `plan` is an opaque per-layer object holding the TMA
+// conv_tc.cu: tcgen05 path (bf16 or fp16 operands, fp32 accumulation).  `plan` is an opaque per-layer object holding the TMA
 // descriptors; created once at finalize time.
 struct TcPlan;
 int tc_plan_create(const ConvArgs& a_maxbatch, int max_batch, TcPlan** out);
@@ -63,6 +72,7 @@ int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hi
 int launch_head_finalize(const float* head /*[B*H*W][ld]*/, int ld, int B, int HW, int num_ratios, int num_classes,
                          int coef_dim, int anchor_offset, int A_total, float* cls, float* box, float* coef,
                          cudaStream_t s);
+int launch_write_activation(const float* in_nchw, int dt, int B, int C, int H, void* out, cudaStream_t s);
 int launch_read_activation(const void* in, int dt, int B, int C, int H, float* out_nchw, cudaStream_t s);
 
 }  // namespace yb

@@ -5,6 +5,7 @@
 #include "layers.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -342,9 +343,13 @@ int pack_conv(yb_net* net, ConvW& c) {
   }
   if (net->act_dt == DT_F32) {
     YB_PROPAGATE(upload(w.data(), w.size() * 4, &c.d_w));
-  } else {
+  } else if (net->act_dt == DT_BF16) {
     std::vector<__nv_bfloat16> wb(w.size());
     for (size_t i = 0; i < w.size(); ++i) wb[i] = __float2bfloat16_rn(w[i]);
+    YB_PROPAGATE(upload(wb.data(), wb.size() * 2, &c.d_w));
+  } else {
+    std::vector<__half> wb(w.size());
+    for (size_t i = 0; i < w.size(); ++i) wb[i] = __float2half_rn(w[i]);
     YB_PROPAGATE(upload(wb.data(), wb.size() * 2, &c.d_w));
   }
   YB_PROPAGATE(upload(bias.data(), bias.size() * 4, (void**)&c.d_b));
@@ -441,7 +446,7 @@ extern "C" int yb_net_set_param(yb_net* net, const char* name, const float* data
 extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   YB_REQUIRE(net, YB_ERR_INVALID, "yb_net_finalize: NULL net");
   YB_REQUIRE(max_batch >= 1 && max_batch <= 4096, YB_ERR_INVALID, "yb_net_finalize: max_batch=%d", max_batch);
-  YB_REQUIRE(precision == YB_PREC_FP32 || precision == YB_PREC_BF16, YB_ERR_INVALID, "yb_net_finalize: precision=%d", precision);
+  YB_REQUIRE(precision == YB_PREC_FP32 || precision == YB_PREC_BF16 || precision == YB_PREC_FP16, YB_ERR_INVALID, "yb_net_finalize: precision=%d", precision);
   for (const auto& p : net->params)
     YB_REQUIRE(p.set, YB_ERR_STATE, "yb_net_finalize: parameter '%s' was never set (strict load)", p.name.c_str());
   int cc_major = 0;
@@ -456,7 +461,7 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   net->d_anchors = net->d_stem_w = net->d_stem_b = nullptr;
 
   net->max_batch = max_batch; net->precision = precision;
-  net->act_dt = precision == YB_PREC_BF16 ? DT_BF16 : DT_F32;
+  net->act_dt = precision == YB_PREC_BF16 ? DT_BF16 : (precision == YB_PREC_FP16 ? DT_F16 : DT_F32);
   plan_memory(net);
   net->slots.resize(net->slot_bytes.size(), nullptr);
   for (size_t s = 0; s < net->slot_bytes.size(); ++s) {
@@ -476,8 +481,8 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
     YB_PROPAGATE(upload(t.data(), t.size() * 4, (void**)&net->d_stem_b));
   }
   YB_PROPAGATE(upload(net->anchors.data(), net->anchors.size() * 4, (void**)&net->d_anchors));
-  // tensor-core plans (bf16 only)
-  if (net->act_dt == DT_BF16) {
+  // tensor-core plans (16-bit operand modes)
+  if (net->act_dt != DT_F32 && !getenv("YOLACT_B200_NO_TC")) {
     for (auto& o : net->ops) {
       if (o.kind != OP_CONV) continue;
       ConvArgs a;
@@ -610,5 +615,89 @@ extern "C" int yb_net_detect_host(yb_net* net, const float* img_host, int batch,
   YB_CHECK_CUDA(cudaMemcpyAsync(out_box, net->d_obox, b * D * 16, cudaMemcpyDeviceToHost, s));
   if (out_coef) YB_CHECK_CUDA(cudaMemcpyAsync(out_coef, net->d_ocoef, b * D * K * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaStreamSynchronize(s));
+  return YB_OK;
+}
+
+// ---- standalone conv layer (tests) ---------------------------------------------------------------
+namespace {
+struct Scratch {
+  std::vector<void*> ptrs;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  int alloc(void** p, size_t bytes) { YB_CHECK_CUDA(cudaMalloc(p, bytes)); YB_CHECK_CUDA(cudaMemset(*p, 0, bytes)); ptrs.push_back(*p); return YB_OK; }
+};
+}  // namespace
+
+extern "C" int yb_conv2d(const float* x, int batch, int cin, int h, const float* w, const float* bias, int cout, int k,
+                         int stride, int relu, const float* residual, int precision, int use_tc, float* out) {
+  YB_REQUIRE(x && w && out, YB_ERR_INVALID, "yb_conv2d: NULL argument");
+  YB_REQUIRE((k == 1 || k == 3) && (stride == 1 || stride == 2), YB_ERR_UNSUPPORTED, "yb_conv2d: k=%d stride=%d", k, stride);
+  YB_REQUIRE(cin % 64 == 0 && cout >= 1 && batch >= 1 && h >= 1, YB_ERR_UNSUPPORTED, "yb_conv2d: cin=%d cout=%d", cin, cout);
+  YB_REQUIRE(precision >= 0 && precision <= 2, YB_ERR_INVALID, "yb_conv2d: precision=%d", precision);
+  const int dt = precision == YB_PREC_BF16 ? DT_BF16 : (precision == YB_PREC_FP16 ? DT_F16 : DT_F32);
+  const size_t esz = dtype_size(dt);
+  const int ho = stride == 2 ? (h - 1) / 2 + 1 : h;
+  const int planes = stride == 2 ? (k == 3 ? 4 : 1) : 1;
+  const int cout_pad = (cout + 15) / 16 * 16, cout_alloc = (cout_pad + 63) / 64 * 64;
+  const int k2 = k * k, Ktot = k2 * cin;
+  Scratch sc;
+  void *d_in = nullptr, *d_split = nullptr, *d_out = nullptr, *d_res = nullptr, *d_w = nullptr; float* d_b = nullptr;
+  const size_t in_rows = (size_t)batch * (h + 2) * (h + 2), out_rows = (size_t)batch * (ho + 2) * (ho + 2);
+  YB_PROPAGATE(sc.alloc(&d_in, in_rows * cin * esz));
+  YB_PROPAGATE(sc.alloc(&d_out, out_rows * cout_pad * esz));
+  YB_PROPAGATE(launch_write_activation(x, dt, batch, cin, h, d_in, nullptr));
+  if (stride == 2) {
+    YB_PROPAGATE(sc.alloc(&d_split, out_rows * planes * cin * esz));
+    YB_PROPAGATE(launch_phase_split(d_in, d_split, dt, batch, cin, h, ho, planes, (long long)out_rows, nullptr));
+  }
+  if (residual) {
+    YB_PROPAGATE(sc.alloc(&d_res, out_rows * cout * esz));
+    YB_PROPAGATE(launch_write_activation(residual, dt, batch, cout, ho, d_res, nullptr));
+  }
+  std::vector<float> wp((size_t)cout_alloc * Ktot, 0.f), bp(cout_alloc, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < k2; ++t) wp[(size_t)co * Ktot + (size_t)t * cin + ci] = w[((size_t)co * cin + ci) * k2 + t];
+    bp[co] = bias ? bias[co] : 0.f;
+  }
+  YB_PROPAGATE(sc.alloc(&d_w, wp.size() * esz));
+  if (dt == DT_F32) YB_CHECK_CUDA(cudaMemcpy(d_w, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
+  else if (dt == DT_BF16) { std::vector<__nv_bfloat16> t(wp.size()); for (size_t i = 0; i < wp.size(); ++i) t[i] = __float2bfloat16_rn(wp[i]); YB_CHECK_CUDA(cudaMemcpy(d_w, t.data(), t.size() * 2, cudaMemcpyHostToDevice)); }
+  else { std::vector<__half> t(wp.size()); for (size_t i = 0; i < wp.size(); ++i) t[i] = __float2half_rn(wp[i]); YB_CHECK_CUDA(cudaMemcpy(d_w, t.data(), t.size() * 2, cudaMemcpyHostToDevice)); }
+  YB_PROPAGATE(sc.alloc((void**)&d_b, bp.size() * 4));
+  YB_CHECK_CUDA(cudaMemcpy(d_b, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = stride == 2 ? d_split : d_in; a.weight = d_w; a.bias = d_b; a.residual = d_res; a.out = d_out;
+  a.act_dt = dt; a.B = batch; a.g.H = ho; a.g.W = ho; a.Cin = cin; a.Cout = cout; a.Cout_pad = cout; a.relu = relu; a.out_mode = 0;
+  YB_REQUIRE(cout % 16 == 0 || !use_tc, YB_ERR_UNSUPPORTED, "yb_conv2d: tc path needs cout %% 16 == 0");
+  const int Wp = ho + 2;
+  if (stride == 1) {
+    a.ntaps = k2;
+    for (int r = 0; r < k; ++r) for (int s = 0; s < k; ++s) a.tap_shift[r * k + s] = k == 1 ? 0 : (r - 1) * Wp + (s - 1);
+    a.in_rows = (long long)out_rows;
+  } else if (k == 1) {
+    a.ntaps = 1; a.tap_shift[0] = 0; a.in_rows = (long long)out_rows;
+  } else {
+    a.ntaps = 9; a.in_rows = (long long)out_rows * 4;
+    for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) {
+      const int pr = r == 1 ? 0 : 1, ps = s == 1 ? 0 : 1, dy = r == 0 ? -1 : 0, dx = s == 0 ? -1 : 0;
+      a.tap_shift[r * 3 + s] = (int)((pr * 2 + ps) * (long long)out_rows) + dy * Wp + dx;
+    }
+  }
+  if (use_tc) {
+    YB_REQUIRE(tc_supported(a), YB_ERR_UNSUPPORTED, "yb_conv2d: shape/precision not supported by the tcgen05 kernel");
+    TcPlan* pl = nullptr;
+    YB_PROPAGATE(tc_plan_create(a, batch, &pl));
+    const int st = launch_conv_tc(pl, a, nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    tc_plan_destroy(pl);
+    YB_PROPAGATE(st);
+    YB_CHECK_CUDA(e);
+  } else {
+    YB_PROPAGATE(launch_conv_simt(a, nullptr));
+  }
+  YB_PROPAGATE(launch_read_activation(d_out, dt, batch, cout, ho, out, nullptr));
+  YB_CHECK_CUDA(cudaDeviceSynchronize());
   return YB_OK;
 }

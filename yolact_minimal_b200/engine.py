@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-PRECISIONS = {'fp32': 0, 'bf16': 1}
+PRECISIONS = {'fp32': 0, 'bf16': 1, 'fp16': 2}
 
 
 class Engine:
