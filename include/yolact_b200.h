@@ -156,6 +156,22 @@ YB_API int yb_net_forward(yb_net* net, const float* img, int batch,
 YB_API int yb_net_read_activation(yb_net* net, const char* name, int batch, float* out, int64_t out_count,
                            int* C, int* H, int* W, void* stream);
 
+/* Per-kernel timing of yb_net_forward with CUDA events on the launching stream (bench.py's
+ * roofline numbers).  While enabled every forward records one event per layer; yb_net_profile
+ * synchronises, aggregates the layers by kernel ("conv_tc", "conv_simt", "stem", ...) over all
+ * forwards since the last call, and resets.  flops / bytes are ALGORITHMIC (2*MAC of the true
+ * convolution; activations + weights + outputs touched once). */
+typedef struct {
+  char name[32];
+  int launches;      /* kernel launches aggregated */
+  int forwards;      /* forwards aggregated */
+  double ms;         /* summed device time */
+  double flops;      /* summed algorithmic flops */
+  double bytes;      /* summed algorithmic bytes */
+} yb_prof_entry;
+YB_API int yb_net_set_profiling(yb_net* net, int enable);
+YB_API int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, int* num_entries);
+
 /* One convolution layer of the engine as a standalone op (unit tests / per-layer parity at the
  * shapes of SURVEY.md App. A): y = [relu]( conv2d(x, w, stride, pad=k/2) + bias [+ residual] ).
  * x [B,Cin,H,H] and residual/out [B,Cout,Ho,Ho] are NCHW float32 on the DEVICE; w [Cout,Cin,k,k]

@@ -128,7 +128,7 @@ def synth_state_dict(arch='res101', num_classes=81, num_ratios=3, seed=0, coef_d
         if bias:
             sd[name + '.bias'] = _u((cout,), -0.05, 0.05)
 
-    def bn(name, c, glo=0.8, ghi=1.6):
+    def bn(name, c, glo=0.8, ghi=1.4):
         sd[name + '.weight'] = _u((c,), glo, ghi)
         sd[name + '.bias'] = _u((c,), -0.1, 0.1)
         sd[name + '.running_mean'] = _u((c,), -0.1, 0.1)
@@ -141,9 +141,9 @@ def synth_state_dict(arch='res101', num_classes=81, num_ratios=3, seed=0, coef_d
         planes = 64 * 2 ** s
         for b in range(nblk):
             p = f'backbone.layers.{s}.{b}'
-            conv(p + '.conv1', planes, inpl, 1, False, gain=1.6); bn(p + '.bn1', planes)
-            conv(p + '.conv2', planes, planes, 3, False, gain=1.6); bn(p + '.bn2', planes)
-            conv(p + '.conv3', planes * 4, planes, 1, False, gain=1.0); bn(p + '.bn3', planes * 4, 0.1, 0.4)
+            conv(p + '.conv1', planes, inpl, 1, False, gain=1.4); bn(p + '.bn1', planes)
+            conv(p + '.conv2', planes, planes, 3, False, gain=1.4); bn(p + '.bn2', planes)
+            conv(p + '.conv3', planes * 4, planes, 1, False, gain=1.0); bn(p + '.bn3', planes * 4, 0.1, 0.3)
             if b == 0:
                 conv(p + '.downsample.0', planes * 4, inpl, 1, False, gain=1.0); bn(p + '.downsample.1', planes * 4, 0.5, 1.0)
             inpl = planes * 4
@@ -159,6 +159,69 @@ def synth_state_dict(arch='res101', num_classes=81, num_ratios=3, seed=0, coef_d
     pl = 'prediction_layers.'
     conv(pl + 'upfeature.0', 256, 256, 3, True, gain=1.3)
     conv(pl + 'bbox_layer', num_ratios * 4, 256, 3, True, gain=0.6)
-    conv(pl + 'conf_layer', num_ratios * num_classes, 256, 3, True, gain=1.5)
+    conv(pl + 'conf_layer', num_ratios * num_classes, 256, 3, True, gain=2.5)
     conv(pl + 'coef_layer.0', num_ratios * coef_dim, 256, 3, True, gain=0.8)
     return sd
+
+
+# ----------------------------------------------------------------------------- 16-bit emulation
+@torch.no_grad()
+def forward_emulated(img, sd, arch='res101', num_classes=81, act=torch.bfloat16):
+    """What a 16-bit-operand / fp32-accumulate pipeline with the engine's rounding points computes
+    (TEST INFRASTRUCTURE): BN folded into fp32 weights which are then rounded to `act`; every
+    stored activation rounded to `act`; accumulation, bias, residual add, ReLU, bilinear
+    interpolation in fp32; head logits / proto output / softmax / tanh in fp32.  Used to separate
+    "the kernels compute the 16-bit pipeline exactly" from "how far a 16-bit pipeline is from
+    the fp32 reference"."""
+    sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    q = lambda t: t.to(act).float()
+
+    def fold(wname, bn):
+        s = sd[bn + '.weight'] / torch.sqrt(sd[bn + '.running_var'] + 1e-5)
+        return sd[wname] * s[:, None, None, None], sd[bn + '.bias'] - sd[bn + '.running_mean'] * s
+
+    w, b = fold('backbone.conv1.weight', 'backbone.bn1')          # the stem runs in fp32 on the fp32 image
+    x = q(F.relu(F.conv2d(img.float(), w, b, stride=2, padding=3)))
+    x = F.max_pool2d(x, 3, 2, 1)
+    outs = []
+    for s, n in enumerate(STAGES[arch]):
+        for bi in range(n):
+            p = f'backbone.layers.{s}.{bi}'
+            st = 2 if (bi == 0 and s > 0) else 1
+            w1, b1 = fold(p + '.conv1.weight', p + '.bn1')
+            o = q(F.relu(F.conv2d(x, q(w1), b1)))
+            w2, b2 = fold(p + '.conv2.weight', p + '.bn2')
+            o = q(F.relu(F.conv2d(o, q(w2), b2, stride=st, padding=1)))
+            w3, b3 = fold(p + '.conv3.weight', p + '.bn3')
+            o = F.conv2d(o, q(w3), b3)
+            r = x
+            if bi == 0:
+                wd, bd = fold(p + '.downsample.0.weight', p + '.downsample.1')
+                r = q(F.conv2d(x, q(wd), bd, stride=st))
+            x = q(F.relu(o + r))
+        outs.append(x)
+    c3, c4, c5 = outs[1:]
+    cv = lambda x, n, **k: F.conv2d(x, q(sd[n + '.weight']), sd[n + '.bias'], **k)
+    up = lambda x, like: F.interpolate(x, size=like.shape[2:], mode='bilinear', align_corners=False)
+    p5_1 = q(cv(c5, 'fpn.lat_layers.2'))
+    l4 = q(cv(c4, 'fpn.lat_layers.1')); p4_1 = q(l4 + up(p5_1, l4))
+    l3 = q(cv(c3, 'fpn.lat_layers.0')); p3_1 = q(l3 + up(p4_1, l3))
+    p5 = q(F.relu(cv(p5_1, 'fpn.pred_layers.2.0', padding=1)))
+    p4 = q(F.relu(cv(p4_1, 'fpn.pred_layers.1.0', padding=1)))
+    p3 = q(F.relu(cv(p3_1, 'fpn.pred_layers.0.0', padding=1)))
+    p6 = q(F.relu(cv(p5, 'fpn.downsample_layers.0.0', stride=2, padding=1)))
+    p7 = q(F.relu(cv(p6, 'fpn.downsample_layers.1.0', stride=2, padding=1)))
+    x = p3
+    for i in (0, 2, 4):
+        x = q(F.relu(cv(x, f'proto_net.proto1.{i}', padding=1)))
+    x = q(F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True))
+    x = q(F.relu(cv(x, 'proto_net.proto2.0', padding=1)))
+    proto = F.relu(cv(x, 'proto_net.proto2.2')).permute(0, 2, 3, 1).contiguous()
+    cl, bx, cf = [], [], []
+    for p in (p3, p4, p5, p6, p7):
+        f = q(F.relu(cv(p, 'prediction_layers.upfeature.0', padding=1)))
+        B = f.size(0)
+        cl.append(cv(f, 'prediction_layers.conf_layer', padding=1).permute(0, 2, 3, 1).reshape(B, -1, num_classes))
+        bx.append(cv(f, 'prediction_layers.bbox_layer', padding=1).permute(0, 2, 3, 1).reshape(B, -1, 4))
+        cf.append(torch.tanh(cv(f, 'prediction_layers.coef_layer.0', padding=1)).permute(0, 2, 3, 1).reshape(B, -1, 32))
+    return F.softmax(torch.cat(cl, 1), -1), torch.cat(bx, 1), torch.cat(cf, 1), proto

@@ -20,6 +20,11 @@ class DetectParams(C.Structure):
                 ('num_classes', C.c_int), ('coef_dim', C.c_int), ('traditional', C.c_int), ('img_size', C.c_float)]
 
 
+class ProfEntry(C.Structure):
+    _fields_ = [('name', C.c_char * 32), ('launches', C.c_int), ('forwards', C.c_int), ('ms', C.c_double),
+                ('flops', C.c_double), ('bytes', C.c_double)]
+
+
 class NetConfig(C.Structure):
     _fields_ = [('depth', C.c_int), ('img_size', C.c_int), ('num_classes', C.c_int), ('num_ratios', C.c_int),
                 ('coef_dim', C.c_int)]
@@ -54,6 +59,8 @@ PROTOTYPES = {
     'yb_net_forward': (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     'yb_net_read_activation': (C.c_int, [vp, C.c_char_p, C.c_int, vp, C.c_int64, C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), vp]),
+    'yb_net_set_profiling': (C.c_int, [vp, C.c_int]),
+    'yb_net_profile': (C.c_int, [vp, C.POINTER(ProfEntry), C.c_int, C.POINTER(C.c_int)]),
     'yb_conv2d': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp]),
     'yb_net_detect_host': (C.c_int, [vp, vp, C.c_int, C.POINTER(DetectParams), vp, vp, vp, vp, vp, vp]),
     'yb_net_last_proto': (vp, [vp]),

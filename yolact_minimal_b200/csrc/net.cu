@@ -81,6 +81,9 @@ struct yb_net {
   int32_t *d_cnt = nullptr, *d_ocls = nullptr, *d_oanc = nullptr; float *d_osc = nullptr, *d_obox = nullptr, *d_ocoef = nullptr;
   int host_batch = 0; int host_maxdet = 0;
   cudaStream_t own_stream = nullptr;
+  bool profiling = false;
+  std::vector<std::vector<cudaEvent_t>> prof_sets;   // one event list per profiled forward
+  std::vector<int> prof_batch;
 
   int add_param(const std::string& n, int64_t count) {
     Param p; p.name = n; p.count = count;
@@ -511,7 +514,17 @@ extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* c
   YB_REQUIRE(batch >= 1 && batch <= net->max_batch, YB_ERR_INVALID, "yb_net_forward: batch=%d outside [1,%d]", batch, net->max_batch);
   cudaStream_t s = (cudaStream_t)stream_;
   const yb_net_config& cfg = net->cfg;
+  std::vector<cudaEvent_t>* evs = nullptr;
+  if (net->profiling && net->prof_sets.size() < 512) {
+    net->prof_sets.emplace_back(net->ops.size() + 1);
+    net->prof_batch.push_back(batch);
+    evs = &net->prof_sets.back();
+    for (auto& e : *evs) YB_CHECK_CUDA(cudaEventCreate(&e));
+    YB_CHECK_CUDA(cudaEventRecord((*evs)[0], s));
+  }
+  int op_index = 0;
   for (const Op& o : net->ops) {
+    ++op_index;
     switch (o.kind) {
       case OP_STEM:
         YB_PROPAGATE(launch_stem(img, net->d_stem_w, net->d_stem_b, act_ptr(net, o.out), net->act_dt, batch, cfg.img_size, net->H1, s));
@@ -547,7 +560,58 @@ extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* c
         break;
       }
     }
+    if (evs) YB_CHECK_CUDA(cudaEventRecord((*evs)[op_index], s));
   }
+  return YB_OK;
+}
+
+extern "C" int yb_net_set_profiling(yb_net* net, int enable) {
+  YB_REQUIRE(net, YB_ERR_INVALID, "yb_net_set_profiling: NULL net");
+  net->profiling = enable != 0;
+  return YB_OK;
+}
+
+extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, int* num_entries) {
+  YB_REQUIRE(net && out && num_entries, YB_ERR_INVALID, "yb_net_profile: NULL argument");
+  static const char* kNames[] = {"conv_tc", "conv_simt", "stem", "maxpool", "phase_split", "upsample_add", "upsample2x", "head_finalize"};
+  const int NK = 8;
+  YB_REQUIRE(max_entries >= NK, YB_ERR_INVALID, "yb_net_profile: need room for %d entries", NK);
+  for (int i = 0; i < NK; ++i) { memset(&out[i], 0, sizeof(out[i])); strncpy(out[i].name, kNames[i], sizeof(out[i].name) - 1); }
+  const size_t esz = dtype_size(net->act_dt);
+  for (size_t f = 0; f < net->prof_sets.size(); ++f) {
+    auto& evs = net->prof_sets[f];
+    const double B = net->prof_batch[f];
+    YB_CHECK_CUDA(cudaEventSynchronize(evs.back()));
+    for (size_t i = 0; i < net->ops.size(); ++i) {
+      const Op& o = net->ops[i];
+      float ms = 0.f;
+      YB_CHECK_CUDA(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+      int k = 0; double flops = 0, bytes = 0;
+      switch (o.kind) {
+        case OP_CONV: {
+          const ConvW& c = net->convs[o.conv];
+          const double Ho = net->acts[o.in].H, px = B * Ho * Ho;
+          k = o.tc ? 0 : 1;
+          flops = 2.0 * px * c.Cout * c.Cin * c.k * c.k;
+          bytes = px * c.Cin * esz * (o.stride == 2 && c.k == 3 ? 4 : 1) + (double)c.Cout * c.Cin * c.k * c.k * esz +
+                  px * c.Cout * (o.out_mode == 1 ? 4 : esz) + (o.res >= 0 ? px * c.Cout * esz : 0);
+          break;
+        }
+        case OP_STEM: k = 2; flops = 2.0 * B * net->H1 * net->H1 * 64 * 147; bytes = B * 3.0 * net->cfg.img_size * net->cfg.img_size * 4 + B * net->H1 * net->H1 * 64.0 * esz; break;
+        case OP_POOL: k = 3; bytes = B * 64.0 * esz * ((double)net->H1 * net->H1 + (double)net->H2 * net->H2); break;
+        case OP_SPLIT: { k = 4; const ActBuf& a = net->acts[o.out]; bytes = 2.0 * B * a.H * a.H * a.planes * a.C * esz; break; }
+        case OP_UPADD: { k = 5; const ActBuf& a = net->acts[o.out]; bytes = 2.25 * B * a.H * a.H * a.C * esz; break; }
+        case OP_UP2X: { k = 6; const ActBuf& a = net->acts[o.out]; bytes = 1.25 * B * a.H * a.H * a.C * esz; break; }
+        case OP_HEADFIN: { k = 7; const ActBuf& a = net->acts[o.in]; bytes = 2.0 * B * a.H * a.H * a.C * 4; break; }
+      }
+      out[k].launches += (o.kind == OP_STEM ? 2 : 1);
+      out[k].ms += ms; out[k].flops += flops; out[k].bytes += bytes;
+    }
+    for (int i = 0; i < NK; ++i) out[i].forwards += 1;
+    for (auto& e : evs) cudaEventDestroy(e);
+  }
+  net->prof_sets.clear(); net->prof_batch.clear();
+  *num_entries = NK;
   return YB_OK;
 }
 

@@ -1,0 +1,71 @@
+"""Multi-GPU inference plumbing: images are independent through forward and post-process, so a
+global batch is sharded across ranks (one process per GPU) with no data-path collective; the
+only exchange is ONE all-gather of fixed-size detection records per batch.
+torch.distributed provides the process group (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from RANK / WORLD_SIZE / MASTER_* (torchrun).
+    Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, init_method='env://', rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(global_batch, rank, world):
+    """Contiguous shard [lo, hi) of a global batch for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def record_width(max_det, coef_dim):
+    return 1 + max_det * (7 + coef_dim)
+
+
+def pack_records(det):
+    """dict from output_utils.detect_batched -> int32 [B, 1 + D*(7+K)] (floats bit-cast)."""
+    B, D = det['cls'].shape
+    K = det['coef'].shape[-1]
+    i32 = lambda t: t.contiguous().view(torch.int32)
+    return torch.cat([det['count'].view(B, 1).to(torch.int32), det['cls'].reshape(B, D), det['anchor'].reshape(B, D),
+                      i32(det['score']).reshape(B, D), i32(det['box']).reshape(B, D * 4),
+                      i32(det['coef']).reshape(B, D * K)], dim=1).contiguous()
+
+
+def unpack_records(rec, max_det, coef_dim):
+    B, D, K = rec.shape[0], max_det, coef_dim
+    o = 1
+    out = {'count': rec[:, 0].contiguous()}
+    out['cls'] = rec[:, o:o + D].contiguous(); o += D
+    out['anchor'] = rec[:, o:o + D].contiguous(); o += D
+    out['score'] = rec[:, o:o + D].contiguous().view(torch.float32); o += D
+    out['box'] = rec[:, o:o + 4 * D].contiguous().view(torch.float32).reshape(B, D, 4); o += 4 * D
+    out['coef'] = rec[:, o:o + K * D].contiguous().view(torch.float32).reshape(B, D, K)
+    return out
+
+
+def gather_detections(det, group=None):
+    """All-gather the detection records of every rank's shard (equal shard sizes).  Returns the
+    dict for the GLOBAL batch in rank order, on every rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return det
+    world = dist.get_world_size(group)
+    D, K = det['cls'].shape[1], det['coef'].shape[-1]
+    rec = pack_records(det)
+    out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
+    return unpack_records(out, D, K)

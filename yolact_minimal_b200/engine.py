@@ -106,6 +106,17 @@ class Engine:
                        'yb_net_read_activation')
         return out
 
+    def set_profiling(self, enable):
+        _lib.check(self.L.yb_net_set_profiling(self.h, 1 if enable else 0), 'yb_net_set_profiling')
+
+    def profile(self):
+        """Per-kernel device time / algorithmic work of the forwards since the last call."""
+        buf = (_lib.ProfEntry * 16)()
+        n = ctypes.c_int()
+        _lib.check(self.L.yb_net_profile(self.h, buf, 16, ctypes.byref(n)), 'yb_net_profile')
+        return {buf[i].name.decode(): dict(launches=buf[i].launches, forwards=buf[i].forwards, ms=buf[i].ms,
+                                           flops=buf[i].flops, bytes=buf[i].bytes) for i in range(n.value)}
+
     def anchors(self):
         a = np.empty((self.num_anchors, 4), np.float32)
         _lib.check(self.L.yb_net_anchors_host(self.h, a.ctypes.data), 'yb_net_anchors_host')
