@@ -270,7 +270,7 @@ def run_ours(args):
                'frac': pp_bytes / (nms_us['stress'] * 1e-6) / 1e9 / pk['hbm'], 'alg_bytes_per_img': pp_bytes, 'regime': 'stress'}
 
     cores = os.cpu_count()
-    cpu_v, cpu_s, cpu_nms_us = cpu_reference_sample(2, 2, cores)
+    cpu_v, cpu_s, cpu_nms_us = (0.0, 0.0, 0.0) if os.environ.get('YB_BENCH_SKIP_CPU') else cpu_reference_sample(2, 2, cores)
     line = {'metric': 'img/s', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision] + ' operands, f32 accumulate',

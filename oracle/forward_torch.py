@@ -180,8 +180,8 @@ def forward_emulated(img, sd, arch='res101', num_classes=81, act=torch.bfloat16)
         s = sd[bn + '.weight'] / torch.sqrt(sd[bn + '.running_var'] + 1e-5)
         return sd[wname] * s[:, None, None, None], sd[bn + '.bias'] - sd[bn + '.running_mean'] * s
 
-    w, b = fold('backbone.conv1.weight', 'backbone.bn1')          # the stem runs in fp32 on the fp32 image
-    x = q(F.relu(F.conv2d(img.float(), w, b, stride=2, padding=3)))
+    w, b = fold('backbone.conv1.weight', 'backbone.bn1')          # stem: im2col GEMM on 16-bit image / weights
+    x = q(F.relu(F.conv2d(q(img.float()), q(w), b, stride=2, padding=3)))
     x = F.max_pool2d(x, 3, 2, 1)
     outs = []
     for s, n in enumerate(STAGES[arch]):

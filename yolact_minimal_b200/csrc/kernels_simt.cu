@@ -22,6 +22,44 @@ template <> struct Act<__nv_bfloat16> {
   static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// 16-byte vector of activations: 4 floats or 8 halfs/bf16s
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* f) { const float4 v = *reinterpret_cast<const float4*>(p); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  static __device__ __forceinline__ void store(float* p, const float* f) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct VecIO<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float* f) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float* f) {
+    uint4 v; __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(fminf(fmaxf(f[2 * i], -65504.f), 65504.f), fminf(fmaxf(f[2 * i + 1], -65504.f), 65504.f));
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+template <> struct VecIO<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+    uint4 v; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+
 __device__ __forceinline__ bool is_halo(long long m, const Geom& g, int& n, int& y, int& x) {
   const int plane = g.plane();
   n = (int)(m / plane);
@@ -171,6 +209,49 @@ __global__ void __launch_bounds__(256) k_stem(const float* __restrict__ img, con
   }
 }
 
+// 16-bit modes: the stem runs on the tensor cores as a GEMM with K = 7*7*3 = 147 padded to 192.
+// This kernel writes the im2col rows in the haloed geometry of the stem OUTPUT:
+// cols[(b, yp, xp)][k], k = (r*7+s)*3 + ci  <- img[b, ci, 2(yp-1)+r-3, 2(xp-1)+s-3]  (0 outside / halo / k >= 147)
+template <typename T>
+__global__ void __launch_bounds__(256) k_stem_im2col(const float* __restrict__ img, T* __restrict__ cols, int B, int S, int H1) {
+  constexpr int KP = 192, N = 8, KV = KP / N;
+  const int Hp = H1 + 2;
+  const long long total = (long long)B * Hp * Hp * KV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kv = (int)(i % KV);
+    long long r = i / KV;
+    const int xp = (int)(r % Hp); r /= Hp;
+    const int yp = (int)(r % Hp);
+    const int b = (int)(r / Hp);
+    float v[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = 0.f;
+    if (yp >= 1 && yp <= H1 && xp >= 1 && xp <= H1) {
+      const int iy0 = 2 * (yp - 1) - 3, ix0 = 2 * (xp - 1) - 3;
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const int k = kv * N + e;
+        if (k < 147) {
+          const int tap = k / 3, ci = k - tap * 3, rr = tap / 7, ss = tap - rr * 7;
+          const int iy = iy0 + rr, ix = ix0 + ss;
+          if (iy >= 0 && iy < S && ix >= 0 && ix < S) v[e] = __ldg(img + (((size_t)b * 3 + ci) * S + iy) * S + ix);
+        }
+      }
+    }
+    VecIO<T>::store(cols + i * N, v);
+  }
+}
+
+int launch_stem_im2col(const float* img, void* cols, int dt, int B, int S, int H1, cudaStream_t s) {
+  YB_REQUIRE(dt != DT_F32, YB_ERR_INVALID, "stem_im2col is for the 16-bit modes");
+  const long long total = (long long)B * (H1 + 2) * (H1 + 2) * 24;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+  if (dt == DT_BF16) k_stem_im2col<__nv_bfloat16><<<blocks, 256, 0, s>>>(img, (__nv_bfloat16*)cols, B, S, H1);
+  else k_stem_im2col<__half><<<blocks, 256, 0, s>>>(img, (__half*)cols, B, S, H1);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
 template <typename T>
 __global__ void k_zero_halo(T* __restrict__ t, int B, int C, int H) {
   // zero the 1-pixel frame of a haloed tensor [B][H+2][H+2][C]
@@ -209,31 +290,36 @@ int launch_stem(const float* img, const float* w, const float* bias, void* out, 
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_maxpool(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout) {
-  const int Hpi = Hin + 2, Hpo = Hout + 2;
-  const long long total = (long long)B * Hpo * Hpo * C;
+  constexpr int N = VecIO<T>::N;
+  const int Hpi = Hin + 2, Hpo = Hout + 2, CV = C / N;
+  const long long total = (long long)B * Hpo * Hpo * CV;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long r = i / C;
+    const int cv = (int)(i % CV);
+    long long r = i / CV;
     const int xp = (int)(r % Hpo); r /= Hpo;
     const int yp = (int)(r % Hpo);
     const int b = (int)(r / Hpo);
-    float m = 0.f;
+    float m[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) m[q] = 0.f;
     if (yp >= 1 && yp <= Hout && xp >= 1 && xp <= Hout) {
       const int y = yp - 1, x = xp - 1;                      // window rows 2y-1..2y+1 -> haloed 2y..2y+2
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const int yy = 2 * y + dy, xx = 2 * x + dx;      // haloed coords, always < Hpi because 2*(Hout-1)+2 <= Hin+1
-          m = fmaxf(m, Act<T>::ld(in + (((size_t)b * Hpi + yy) * Hpi + xx) * C + c));
+          float v[N];
+          VecIO<T>::load(in + (((size_t)b * Hpi + 2 * y + dy) * Hpi + 2 * x + dx) * C + cv * N, v);
+#pragma unroll
+          for (int q = 0; q < N; ++q) m[q] = fmaxf(m[q], v[q]);
         }
     }
-    Act<T>::st(out + i, m);
+    VecIO<T>::store(out + i * N, m);
   }
 }
 
 int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s) {
-  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C;
+  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C / 4;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
   YB_DISPATCH_DT(dt, (k_maxpool<T><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout)));
   YB_CHECK_LAUNCH();
@@ -247,27 +333,30 @@ int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int
 template <typename T>
 __global__ void k_phase_split(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout,
                               int nplanes, long long plane_stride_rows) {
-  const int Hpi = Hin + 2, Hpo = Hout + 2;
-  const long long per_plane = (long long)B * Hpo * Hpo * C;
+  constexpr int N = VecIO<T>::N;
+  const int Hpi = Hin + 2, Hpo = Hout + 2, CV = C / N;
+  const long long per_plane = (long long)B * Hpo * Hpo * CV;
   const long long total = per_plane * nplanes;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int pl = (int)(i / per_plane);
     long long r = i - pl * per_plane;
-    const int c = (int)(r % C); r /= C;
+    const int cv = (int)(r % CV); r /= CV;
     const int xp = (int)(r % Hpo); r /= Hpo;
     const int yp = (int)(r % Hpo);
     const int b = (int)(r / Hpo);
     const int p = pl >> 1, q = pl & 1;
     const int iy = 2 * (yp - 1) + p, ix = 2 * (xp - 1) + q;
-    float v = 0.f;
-    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) v = Act<T>::ld(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + c);
-    Act<T>::st(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + c, v);
+    float v[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = 0.f;
+    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) VecIO<T>::load(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + cv * N, v);
+    VecIO<T>::store(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N, v);
   }
 }
 
 int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
                        long long plane_stride_rows, cudaStream_t s) {
-  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C * nplanes;
+  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C * nplanes / 4;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
   YB_DISPATCH_DT(dt, (k_phase_split<T><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, nplanes, plane_stride_rows)));
   YB_CHECK_LAUNCH();
@@ -287,30 +376,46 @@ __device__ __forceinline__ void src_index(int dst, float scale, bool align, int 
 
 template <typename T, bool kAdd, bool kAlign>
 __global__ void k_bilinear(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int Hs, int Hd, float scale) {
-  const int Hps = Hs + 2, Hpd = Hd + 2;
-  const long long total = (long long)B * Hpd * Hpd * C;
+  constexpr int N = VecIO<T>::N;
+  const int Hps = Hs + 2, Hpd = Hd + 2, CV = C / N;
+  const long long total = (long long)B * Hpd * Hpd * CV;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long r = i / C;
+    const int cv = (int)(i % CV);
+    long long r = i / CV;
     const int xp = (int)(r % Hpd); r /= Hpd;
     const int yp = (int)(r % Hpd);
     const int b = (int)(r / Hpd);
     const bool halo = yp == 0 || yp == Hd + 1 || xp == 0 || xp == Hd + 1;
-    if (halo) { if (!kAdd) Act<T>::st(dst + i, 0.f); continue; }
+    float v[N];
+    if (halo) {
+      if (!kAdd) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = 0.f;
+        VecIO<T>::store(dst + i * N, v);
+      }
+      continue;
+    }
     int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
     src_index(yp - 1, scale, kAlign, Hs, y0, y1, ly0, ly1);
     src_index(xp - 1, scale, kAlign, Hs, x0, x1, lx0, lx1);
-    const T* sb = src + (size_t)b * Hps * Hps * C + c;
-    const float v00 = Act<T>::ld(sb + ((size_t)(y0 + 1) * Hps + x0 + 1) * C), v01 = Act<T>::ld(sb + ((size_t)(y0 + 1) * Hps + x1 + 1) * C);
-    const float v10 = Act<T>::ld(sb + ((size_t)(y1 + 1) * Hps + x0 + 1) * C), v11 = Act<T>::ld(sb + ((size_t)(y1 + 1) * Hps + x1 + 1) * C);
-    float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-    if (kAdd) v += Act<T>::ld(dst + i);
-    Act<T>::st(dst + i, v);
+    const T* sb = src + (size_t)b * Hps * Hps * C + cv * N;
+    float v00[N], v01[N], v10[N], v11[N];
+    VecIO<T>::load(sb + ((size_t)(y0 + 1) * Hps + x0 + 1) * C, v00);
+    VecIO<T>::load(sb + ((size_t)(y0 + 1) * Hps + x1 + 1) * C, v01);
+    VecIO<T>::load(sb + ((size_t)(y1 + 1) * Hps + x0 + 1) * C, v10);
+    VecIO<T>::load(sb + ((size_t)(y1 + 1) * Hps + x1 + 1) * C, v11);
+    if (kAdd) VecIO<T>::load(dst + i * N, v);
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      const float t = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
+      v[e] = kAdd ? v[e] + t : t;
+    }
+    VecIO<T>::store(dst + i * N, v);
   }
 }
 
 int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, int Hc, int Hf, cudaStream_t s) {
-  const long long total = (long long)B * (Hf + 2) * (Hf + 2) * C;
+  const long long total = (long long)B * (Hf + 2) * (Hf + 2) * C / 4;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
   const float scale = (float)Hc / (float)Hf;
   YB_DISPATCH_DT(dt, (k_bilinear<T, true, false><<<blocks, 256, 0, s>>>((const T*)coarse, (T*)fine, B, C, Hc, Hf, scale)));
@@ -321,7 +426,7 @@ int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, in
 // protonet: bilinear x2, align_corners=True (modules/yolact.py:43,:51)
 int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hin, cudaStream_t s) {
   const int Hout = 2 * Hin;
-  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C;
+  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C / 4;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
   const float scale = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
   YB_DISPATCH_DT(dt, (k_bilinear<T, false, true><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, scale)));

@@ -64,6 +64,7 @@ bool tc_supported(const ConvArgs& a);
 
 int launch_stem(const float* img_nchw, const float* w /*[7][7][3][64]*/, const float* bias, void* out, int out_dt,
                 int B, int S, int H1, cudaStream_t s);
+int launch_stem_im2col(const float* img_nchw, void* cols /*[B*(H1+2)^2][192]*/, int dt, int B, int S, int H1, cudaStream_t s);
 int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s);
 int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
                        long long plane_stride_rows, cudaStream_t s);

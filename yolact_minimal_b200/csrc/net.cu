@@ -51,6 +51,7 @@ struct Op {
   int conv = -1;               // index into convs
   int stride = 1, relu = 0, out_mode = 0, ext = EXT_NONE;
   int level = 0;               // head level
+  int aux = -1;                // extra scratch activation (stem: im2col rows)
   TcPlan* tc = nullptr;
 };
 
@@ -75,6 +76,9 @@ struct yb_net {
   float* d_anchors = nullptr;
   float* d_stem_w = nullptr;                // [7][7][3][64]
   float* d_stem_b = nullptr;
+  void* d_stem_w16 = nullptr;               // 16-bit modes: [64][192] GEMM weights (k = (r*7+s)*3+ci)
+  float* d_stem_b16 = nullptr;
+  ConvArgs stem_args{};
   // scratch for yb_net_detect_host
   float *d_img = nullptr, *d_cls = nullptr, *d_box = nullptr, *d_coef = nullptr, *d_proto = nullptr;
   void* d_ws = nullptr; size_t ws_bytes = 0;
@@ -143,7 +147,8 @@ void build_program(yb_net* net) {
   net->add_param("backbone.conv1.weight", 64 * 3 * 7 * 7);
   for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) net->add_param(std::string("backbone.bn1") + s, 64);
   const int stem = new_act(net, 64, net->H1);
-  { Op o; o.kind = OP_STEM; o.out = stem; net->ops.push_back(o); }
+  const int stem_cols = new_act(net, 192, net->H1);
+  { Op o; o.kind = OP_STEM; o.out = stem; o.aux = stem_cols; net->ops.push_back(o); }
   int x = new_act(net, 64, net->H2);
   { Op o; o.kind = OP_POOL; o.in = stem; o.out = x; net->ops.push_back(o); }
 
@@ -263,7 +268,7 @@ void plan_memory(yb_net* net) {
   for (auto& a : acts) { a.first = 1 << 30; a.last = -1; }
   for (int i = 0; i < (int)net->ops.size(); ++i) {
     const Op& o = net->ops[i];
-    for (int t : {o.in, o.out, o.res}) {
+    for (int t : {o.in, o.out, o.res, o.aux}) {
       if (t < 0) continue;
       acts[t].first = acts[t].first < i ? acts[t].first : i;
       acts[t].last = acts[t].last > i ? acts[t].last : i;
@@ -417,7 +422,7 @@ extern "C" void yb_net_destroy(yb_net* net) {
   for (void* p : net->slots) cudaFree(p);
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); }
   for (auto& o : net->ops) tc_plan_destroy(o.tc);
-  for (void* p : {(void*)net->d_anchors, (void*)net->d_stem_w, (void*)net->d_stem_b, (void*)net->d_img, (void*)net->d_cls,
+  for (void* p : {(void*)net->d_anchors, (void*)net->d_stem_w, (void*)net->d_stem_b, net->d_stem_w16, (void*)net->d_stem_b16, (void*)net->d_img, (void*)net->d_cls,
                   (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws, (void*)net->d_cnt, (void*)net->d_ocls,
                   (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
     cudaFree(p);
@@ -460,8 +465,8 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   net->slots.clear();
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); c.d_w = nullptr; c.d_b = nullptr; }
   for (auto& o : net->ops) { tc_plan_destroy(o.tc); o.tc = nullptr; }
-  cudaFree(net->d_anchors); cudaFree(net->d_stem_w); cudaFree(net->d_stem_b);
-  net->d_anchors = net->d_stem_w = net->d_stem_b = nullptr;
+  cudaFree(net->d_anchors); cudaFree(net->d_stem_w); cudaFree(net->d_stem_b); cudaFree(net->d_stem_w16); cudaFree(net->d_stem_b16);
+  net->d_anchors = net->d_stem_w = net->d_stem_b = net->d_stem_b16 = nullptr; net->d_stem_w16 = nullptr;
 
   net->max_batch = max_batch; net->precision = precision;
   net->act_dt = precision == YB_PREC_BF16 ? DT_BF16 : (precision == YB_PREC_FP16 ? DT_F16 : DT_F32);
@@ -486,6 +491,25 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   YB_PROPAGATE(upload(net->anchors.data(), net->anchors.size() * 4, (void**)&net->d_anchors));
   // tensor-core plans (16-bit operand modes)
   if (net->act_dt != DT_F32 && !getenv("YOLACT_B200_NO_TC")) {
+    {  // stem as a GEMM over im2col rows: [B*(H1+2)^2][192] x [192][64]
+      std::vector<float> sc, sh, w((size_t)64 * 192, 0.f);
+      bn_fold(net, "backbone.bn1", 64, sc, sh);
+      const auto& src = net->P_("backbone.conv1.weight");
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int t = 0; t < 49; ++t) w[(size_t)co * 192 + t * 3 + ci] = src[((size_t)co * 3 + ci) * 49 + t] * sc[co];
+      if (net->act_dt == DT_BF16) { std::vector<__nv_bfloat16> t(w.size()); for (size_t i = 0; i < w.size(); ++i) t[i] = __float2bfloat16_rn(w[i]); YB_PROPAGATE(upload(t.data(), t.size() * 2, &net->d_stem_w16)); }
+      else { std::vector<__half> t(w.size()); for (size_t i = 0; i < w.size(); ++i) t[i] = __float2half_rn(w[i]); YB_PROPAGATE(upload(t.data(), t.size() * 2, &net->d_stem_w16)); }
+      YB_PROPAGATE(upload(sh.data(), sh.size() * 4, (void**)&net->d_stem_b16));
+      Op& so = net->ops[0];
+      ConvArgs& a = net->stem_args;
+      memset(&a, 0, sizeof(a));
+      a.in = act_ptr(net, so.aux); a.weight = net->d_stem_w16; a.bias = net->d_stem_b16; a.out = act_ptr(net, so.out);
+      a.act_dt = net->act_dt; a.B = max_batch; a.g.H = net->H1; a.g.W = net->H1; a.Cin = 192; a.Cout = 64; a.Cout_pad = 64;
+      a.ntaps = 1; a.tap_shift[0] = 0; a.relu = 1; a.out_mode = 0;
+      a.in_rows = (long long)max_batch * (net->H1 + 2) * (net->H1 + 2);
+      YB_PROPAGATE(tc_plan_create(a, max_batch, &so.tc));
+    }
     for (auto& o : net->ops) {
       if (o.kind != OP_CONV) continue;
       ConvArgs a;
@@ -527,7 +551,14 @@ extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* c
     ++op_index;
     switch (o.kind) {
       case OP_STEM:
-        YB_PROPAGATE(launch_stem(img, net->d_stem_w, net->d_stem_b, act_ptr(net, o.out), net->act_dt, batch, cfg.img_size, net->H1, s));
+        if (o.tc) {
+          YB_PROPAGATE(launch_stem_im2col(img, act_ptr(net, o.aux), net->act_dt, batch, cfg.img_size, net->H1, s));
+          ConvArgs a = net->stem_args;
+          a.B = batch;
+          YB_PROPAGATE(launch_conv_tc(o.tc, a, s));
+        } else {
+          YB_PROPAGATE(launch_stem(img, net->d_stem_w, net->d_stem_b, act_ptr(net, o.out), net->act_dt, batch, cfg.img_size, net->H1, s));
+        }
         break;
       case OP_POOL:
         YB_PROPAGATE(launch_maxpool(act_ptr(net, o.in), act_ptr(net, o.out), net->act_dt, batch, 64, net->H1, net->H2, s));
@@ -578,6 +609,9 @@ extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, 
   YB_REQUIRE(max_entries >= NK, YB_ERR_INVALID, "yb_net_profile: need room for %d entries", NK);
   for (int i = 0; i < NK; ++i) { memset(&out[i], 0, sizeof(out[i])); strncpy(out[i].name, kNames[i], sizeof(out[i].name) - 1); }
   const size_t esz = dtype_size(net->act_dt);
+  FILE* dump = nullptr;
+  if (const char* path = getenv("YOLACT_B200_PROFILE_DUMP")) dump = fopen(path, "w");
+  if (dump) fprintf(dump, "forward,op,kind,tc,cin,cout,k,stride,h_out,batch,ms,gflop\n");
   for (size_t f = 0; f < net->prof_sets.size(); ++f) {
     auto& evs = net->prof_sets[f];
     const double B = net->prof_batch[f];
@@ -604,12 +638,18 @@ extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, 
         case OP_UP2X: { k = 6; const ActBuf& a = net->acts[o.out]; bytes = 1.25 * B * a.H * a.H * a.C * esz; break; }
         case OP_HEADFIN: { k = 7; const ActBuf& a = net->acts[o.in]; bytes = 2.0 * B * a.H * a.H * a.C * 4; break; }
       }
+      if (dump) {
+        const ConvW* c = o.kind == OP_CONV ? &net->convs[o.conv] : nullptr;
+        fprintf(dump, "%zu,%zu,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.4f\n", f, i, (int)o.kind, o.tc ? 1 : 0, c ? c->Cin : 0, c ? c->Cout_pad : 0,
+                c ? c->k : 0, o.stride, o.kind == OP_CONV ? net->acts[o.in].H : 0, (int)B, ms, flops * 1e-9);
+      }
       out[k].launches += (o.kind == OP_STEM ? 2 : 1);
       out[k].ms += ms; out[k].flops += flops; out[k].bytes += bytes;
     }
     for (int i = 0; i < NK; ++i) out[i].forwards += 1;
     for (auto& e : evs) cudaEventDestroy(e);
   }
+  if (dump) fclose(dump);
   net->prof_sets.clear(); net->prof_batch.clear();
   *num_entries = NK;
   return YB_OK;
