@@ -33,6 +33,18 @@ ARCH, IMG, BATCH = 'res101', 550, 64
 GFLOP_PER_IMG = 164.68          # algorithmic 2*MAC of the reference forward, res101 @ 550
 
 
+def host_cores():
+    """CPU threads this process can actually use: min(affinity, cgroup cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -44,7 +56,7 @@ def peaks():
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
@@ -59,24 +71,31 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken between wall-clock times t0 and t1 (the timed region)."""
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
         self.proc.terminate()
         self.t.join(2)
-        sm, mx, reasons = [], None, set()
+        import datetime
+        sm, pw, mx, reasons = [], [], None, set()
         for l in self.lines:
             f = [x.strip() for x in l.split(',')]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                    continue
+                sm.append(float(f[1])); mx = float(f[2]); pw.append(float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'power_w_max': max(pw) if pw else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -106,12 +125,12 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    n_img = 2
+    cores = host_cores()
+    n_img = 4
     for _ in range(args.warmup):
         pass                                                        # the sample's own warm-up forward is inside
     vals, t_all, nms_us = [], 0.0, 0.0
-    steps = max(1, min(args.steps, 8))                              # bounded: each step is a 2-image sample
+    steps = max(1, min(args.steps, 20))                             # bounded: each step is a 4-image sample
     for _ in range(steps):
         v, dt, nu = cpu_reference_sample(n_img, 1, cores)
         vals.append(v); t_all += dt; nms_us = nu
@@ -167,6 +186,8 @@ def run_ours(args):
             det = ydist.gather_detections(det)
         return det, (cls, box, coef, proto)
 
+    sampler = ClockSampler(local)
+    sampler.start()                                                 # nvidia-smi needs ~0.5 s to start: begin before warm-up
     for i in range(W):
         det, outs = step(i)
     torch.cuda.synchronize()
@@ -174,12 +195,11 @@ def run_ours(args):
     # ---- timed region: device-resident inputs --------------------------------------------------
     eng.set_profiling(True)
     eng.profile()
-    sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     l0 = _lib.launch_count()
+    wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(K):
@@ -188,8 +208,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1)
     launches = _lib.launch_count() - l0
     prof = eng.profile()
     eng.set_profiling(False)
@@ -269,8 +290,8 @@ def run_ours(args):
                'achieved': pp_bytes / (nms_us['stress'] * 1e-6) / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s',
                'frac': pp_bytes / (nms_us['stress'] * 1e-6) / 1e9 / pk['hbm'], 'alg_bytes_per_img': pp_bytes, 'regime': 'stress'}
 
-    cores = os.cpu_count()
-    cpu_v, cpu_s, cpu_nms_us = (0.0, 0.0, 0.0) if os.environ.get('YB_BENCH_SKIP_CPU') else cpu_reference_sample(2, 2, cores)
+    cores = host_cores()
+    cpu_v, cpu_s, cpu_nms_us = (0.0, 0.0, 0.0) if os.environ.get('YB_BENCH_SKIP_CPU') else cpu_reference_sample(4, 8, cores)
     line = {'metric': 'img/s', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision] + ' operands, f32 accumulate',
@@ -283,7 +304,7 @@ def run_ours(args):
             'gflop_per_img': GFLOP_PER_IMG,
             'fast_nms_us_per_img': nms_us, 'roofline': roofline, 'roofline_postprocess': pp_roof, 'kernel_breakdown': breakdown,
             'cpu_baseline': {'value': cpu_v, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'2 reps x 2 images ({cpu_s:.1f} s): torch fp32 CPU forward + numpy nms()',
+                             'sample': f'8 reps x 4 images ({cpu_s:.1f} s): torch fp32 CPU forward + numpy nms()',
                              'fast_nms_us_per_img': cpu_nms_us},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_fp32_oracle_max_abs_err': parity}
     print(json.dumps(line))
@@ -292,7 +313,7 @@ def run_ours(args):
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--precision', default=os.environ.get('YOLACT_B200_PRECISION', 'fp16'), choices=['fp16', 'bf16', 'fp32'])
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])

@@ -26,6 +26,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_A_STAGE = TC_BM * TC_BK * 2;   // 16 KiB
+constexpr uint32_t TC_EPI_TILE = TC_BM * 32 * 2;     // 8 KiB: 128 rows x 32 columns of 16-bit outputs
 
 struct TcParams {
   long long M;            // rows to produce (B * plane)
@@ -38,6 +39,7 @@ struct TcParams {
   int stages;
   int Cout, Cout_pad, relu, out_mode;
   int is_f16;             // operands fp16 (else bf16)
+  int tma_epi;            // out_mode 0 && BN % 32 == 0: smem-staged TMA stores (+ TMA-prefetched residual)
   Geom g;
   const float* bias;
   const void* residual;
@@ -45,8 +47,8 @@ struct TcParams {
 };
 
 struct TcPlan {
-  CUtensorMap tmA, tmB;
-  int BN, stages, tmem_cols;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  int BN, stages, tmem_cols, tma_epi;
   size_t smem_bytes;
 };
 
@@ -78,6 +80,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -193,17 +204,21 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024B alignment
   const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_stage);
+  uint8_t* sOut = sB + (size_t)p.stages * b_stage;                 // [2][128 rows x 64 B], SWIZZLE_64B (TMA epilogue only)
+  uint8_t* sRes = sOut + (p.tma_epi ? 2 * TC_EPI_TILE : 0);        // [2][128 rows x 64 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.tma_epi ? 2 * TC_EPI_TILE : 0));
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -213,7 +228,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); mbar_init(&res_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -277,7 +292,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
+    const bool elected = threadIdx.x == 64;                      // warp 2, lane 0
+    const bool has_res = p.residual != nullptr;
+    const int chunks_per_tile = p.BN / 32;
     int acc = 0; uint32_t acc_phase = 0;
+    // running chunk sequence over all tiles of this CTA (TMA epilogue): seq -> (tile, chunk)
+    long long seq = 0;
+    const long long my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const long long total_seq = my_tiles * chunks_per_tile;
+    auto issue_res_load = [&](long long sq) {
+      const int t = (int)(sq / chunks_per_tile), c = (int)(sq - (long long)t * chunks_per_tile);
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int buf = (int)(sq & 1);
+      mbar_expect_tx(&res_full[buf], TC_EPI_TILE);
+      tma_load_2d(sRes + buf * TC_EPI_TILE, &tmRes, nt * p.BN + c * 32, mt * TC_BM, &res_full[buf]);
+    };
+    if (p.tma_epi && has_res && elected) {
+      if (total_seq > 0) issue_res_load(0);
+      if (total_seq > 1) issue_res_load(1);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const long long m = (long long)m_tile * TC_BM + row_in_tile;
@@ -295,18 +329,81 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
       const int n0 = n_tile * p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t r[32];
-        if (c0 + 32 <= p.BN) {
-          tmem_ld32(t_base + c0, r);
+      if (p.tma_epi) {
+        const uint32_t sw = (uint32_t)((row_in_tile >> 1) & 3);      // SWIZZLE_64B: 16B chunk index ^= address bits [7,8]
+        for (int c = 0; c < chunks_per_tile; ++c, ++seq) {
+          const int buf = (int)(seq & 1);
+          uint32_t r[32];
+          tmem_ld32(t_base + c * 32, r);
           tmem_ld_wait();
-          if (p.is_f16) epilogue_chunk<32, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
-          else epilogue_chunk<32, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
-        } else {
-          tmem_ld16(t_base + c0, r);
-          tmem_ld_wait();
-          if (p.is_f16) epilogue_chunk<16, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
-          else epilogue_chunk<16, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
+          float v[32];
+          const int col = n0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+            v[i] = __uint_as_float(r[i]) + b.x; v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
+            v[i + 2] = __uint_as_float(r[i + 2]) + b.z; v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+          }
+          if (has_res) {
+            mbar_wait(&res_full[buf], (uint32_t)((seq >> 1) & 1));
+            const uint8_t* rrow = sRes + buf * TC_EPI_TILE + row_in_tile * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)j ^ sw) << 4));
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = p.is_f16 ? unpack2<true>(rw[q]) : unpack2<false>(rw[q]);
+                v[j * 8 + 2 * q] += f.x; v[j * 8 + 2 * q + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (halo || !valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          // the store issued from sOut[buf] two chunks ago must have finished reading smem
+          if (elected) bulk_wait_read<1>();
+          epi_barrier();
+          uint8_t* orow = sOut + buf * TC_EPI_TILE + row_in_tile * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            if (p.is_f16) {
+              pk.x = pack2<true>(v[j * 8], v[j * 8 + 1]); pk.y = pack2<true>(v[j * 8 + 2], v[j * 8 + 3]);
+              pk.z = pack2<true>(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack2<true>(v[j * 8 + 6], v[j * 8 + 7]);
+            } else {
+              pk.x = pack2<false>(v[j * 8], v[j * 8 + 1]); pk.y = pack2<false>(v[j * 8 + 2], v[j * 8 + 3]);
+              pk.z = pack2<false>(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack2<false>(v[j * 8 + 6], v[j * 8 + 7]);
+            }
+            *reinterpret_cast<uint4*>(orow + (((uint32_t)j ^ sw) << 4)) = pk;
+          }
+          fence_async_smem();
+          epi_barrier();
+          if (elected) {
+            tma_store_2d(&tmOut, sOut + buf * TC_EPI_TILE, col, m_tile * TC_BM);
+            bulk_commit();
+            if (has_res && seq + 2 < total_seq) issue_res_load(seq + 2);     // sRes[buf] was consumed before the barrier
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t r[32];
+          if (c0 + 32 <= p.BN) {
+            tmem_ld32(t_base + c0, r);
+            tmem_ld_wait();
+            if (p.is_f16) epilogue_chunk<32, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
+            else epilogue_chunk<32, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
+          } else {
+            tmem_ld16(t_base + c0, r);
+            tmem_ld_wait();
+            if (p.is_f16) epilogue_chunk<16, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
+            else epilogue_chunk<16, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
+          }
         }
       }
       tc_fence_before();
@@ -314,6 +411,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_epi && elected) bulk_wait<0>();                     // all output tiles landed before the CTA exits
   }
 
   tc_fence_before();
@@ -341,15 +439,16 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows, bool f16) {
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows, bool f16,
+                    uint32_t box_inner = TC_BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   YB_REQUIRE(enc != nullptr, YB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[2] = {inner, rows};
   const cuuint64_t strides[1] = {inner * 2};
-  const cuuint32_t box[2] = {TC_BK, box_rows};
+  const cuuint32_t box[2] = {box_inner, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   YB_REQUIRE(r == CUDA_SUCCESS, YB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu box_rows=%u", (int)r,
              (unsigned long long)inner, (unsigned long long)rows, box_rows);
@@ -371,23 +470,31 @@ bool tc_supported(const ConvArgs& a) {
 }
 
 int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
-  (void)max_batch;
   YB_REQUIRE(tc_supported(a), YB_ERR_UNSUPPORTED, "tc_plan_create: unsupported conv Cin=%d Cout_pad=%d", a.Cin, a.Cout_pad);
   TcPlan* pl = new TcPlan();
   pl->BN = pick_bn(a.Cout_pad);
   int cols = 32;
   while (cols < 2 * pl->BN) cols <<= 1;
   pl->tmem_cols = cols;
+  pl->tma_epi = (a.out_mode == 0 && pl->BN % 32 == 0) ? 1 : 0;
   const size_t per_stage = TC_A_STAGE + (size_t)pl->BN * TC_BK * 2;
-  int stages = (int)((200 * 1024) / per_stage);
+  const size_t epi_bytes = pl->tma_epi ? 4 * TC_EPI_TILE : 0;
+  const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + epi_bytes;
+  int stages = (int)((227 * 1024 - fixed) / per_stage);
   if (stages > 8) stages = 8;
   pl->stages = stages;
-  pl->smem_bytes = (size_t)stages * per_stage + 1024 /*align*/ + 256 /*barriers*/;
+  pl->smem_bytes = (size_t)stages * per_stage + fixed;
   const int Ktot = a.ntaps * a.Cin;
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
   int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, TC_BM, f16);
   if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)pl->BN, f16);
+  pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;                      // placeholders when the TMA epilogue is off
+  if (s == YB_OK && pl->tma_epi) {
+    const uint64_t out_rows = (uint64_t)max_batch * a.g.plane();
+    s = make_map(&pl->tmOut, a.out, (uint64_t)a.Cout, out_rows, TC_BM, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (s == YB_OK && a.residual) s = make_map(&pl->tmRes, a.residual, (uint64_t)a.Cout, out_rows, TC_BM, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  }
   if (s != YB_OK) { delete pl; return s; }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -409,12 +516,12 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
-  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16;
+  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
-  k_conv_tc<<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, p);
+  k_conv_tc<<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
