@@ -18,6 +18,7 @@
 
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace yb {
@@ -40,6 +41,8 @@ struct TcParams {
   int Cout, Cout_pad, relu, out_mode;
   int is_f16;             // operands fp16 (else bf16)
   int tma_epi;            // out_mode 0 && BN % 32 == 0: smem-staged TMA stores (+ TMA-prefetched residual)
+  int nres;               // residual prefetch buffers (0 if none)
+  int b_resident;         // weights of the CTA's N tile stay in shared memory for all its M tiles
   Geom g;
   const float* bias;
   const void* residual;
@@ -48,7 +51,7 @@ struct TcParams {
 
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  int BN, stages, tmem_cols, tma_epi;
+  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult;
   size_t smem_bytes;
 };
 
@@ -203,32 +206,49 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
   }
 }
 
+// CTA-local iteration i -> tile coordinates.  Streaming mode: tiles round-robin over the grid with
+// the N tiles of one M tile adjacent (A shared through L2).  Weight-resident mode: the CTA owns one
+// N tile for its whole life (its weights stay in shared memory) and strides over M tiles.
+__device__ __forceinline__ bool tile_at(const TcParams& p, int i, int& m_tile, int& n_tile) {
+  if (p.b_resident) {
+    n_tile = (int)blockIdx.x % p.n_tiles;
+    m_tile = (int)blockIdx.x / p.n_tiles + i * ((int)gridDim.x / p.n_tiles);
+    return m_tile < p.m_tiles;
+  }
+  const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+  if (tile >= p.m_tiles * p.n_tiles) return false;
+  m_tile = tile / p.n_tiles;
+  n_tile = tile - m_tile * p.n_tiles;
+  return true;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024B alignment
   const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;
-  uint8_t* sOut = sB + (size_t)p.stages * b_stage;                 // [2][128 rows x 64 B], SWIZZLE_64B (TMA epilogue only)
-  uint8_t* sRes = sOut + (p.tma_epi ? 2 * TC_EPI_TILE : 0);        // [2][128 rows x 64 B]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.tma_epi ? 2 * TC_EPI_TILE : 0));
-  uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;      // [2]
+  const int num_kb = p.ntaps * p.kb_per_tap;
+  uint8_t* sA = smem;                                                               // [stages][16 KiB]
+  uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;                               // [stages | num_kb][BN x 128 B]
+  uint8_t* sOut = sB + (size_t)(p.b_resident ? num_kb : p.stages) * b_stage;        // [2][128 rows x 64 B], SWIZZLE_64B
+  uint8_t* sRes = sOut + (p.tma_epi ? 2 * TC_EPI_TILE : 0);                         // [nres][128 rows x 64 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (size_t)p.nres * TC_EPI_TILE);
+  uint64_t* empty = full + 8;
+  uint64_t* tmem_full = empty + 8;             // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint64_t* res_full = tmem_empty + 2;         // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_full = tmem_empty + 2;         // [8]
+  uint64_t* b_full = res_full + 8;             // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  const int num_kb = p.ntaps * p.kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); mbar_init(&res_full[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&res_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -243,17 +263,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
+      int m_tile, n_tile;
+      if (p.b_resident && tile_at(p, 0, m_tile, n_tile)) {
+        // the CTA's whole weight slice [BN x Ktot], loaded once
+        mbar_expect_tx(b_full, (uint32_t)num_kb * b_stage);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + (size_t)kb * b_stage, &tmB, kb * TC_BK, n_tile * p.BN, b_full);
+      }
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const uint32_t tx = p.b_resident ? TC_A_STAGE : TC_A_STAGE + b_stage;
+      for (int i = 0; tile_at(p, i, m_tile, n_tile); ++i) {
         const int m0 = m_tile * TC_BM, n0 = n_tile * p.BN;
         for (int t = 0; t < p.ntaps; ++t) {
           const int row = m0 + p.tap_shift[t];
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], TC_A_STAGE + b_stage);
+            mbar_expect_tx(&full[stage], tx);
             tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmA, kb * TC_BK, row, &full[stage]);
-            tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0, &full[stage]);
+            if (!p.b_resident) tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0, &full[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -267,7 +293,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_tile, n_tile;
+      if (p.b_resident && tile_at(p, 0, m_tile, n_tile)) mbar_wait(b_full, 0);
+      for (int i = 0; tile_at(p, i, m_tile, n_tile); ++i) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
@@ -275,10 +303,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
-          const uint64_t db = umma_desc(smem_u32(sB + (size_t)stage * b_stage));
+          const uint64_t db = umma_desc(smem_u32(sB + (size_t)(p.b_resident ? kb : stage) * b_stage));
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);                   // smem stage free once these MMAs retire
@@ -295,25 +323,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const bool elected = threadIdx.x == 64;                      // warp 2, lane 0
     const bool has_res = p.residual != nullptr;
     const int chunks_per_tile = p.BN / 32;
+    const int nres = p.nres;
     int acc = 0; uint32_t acc_phase = 0;
-    // running chunk sequence over all tiles of this CTA (TMA epilogue): seq -> (tile, chunk)
+    // running chunk sequence over all tiles of this CTA (TMA epilogue): seq -> (local tile index, chunk)
+    int my_tiles = 0;
+    { int mt, nt; while (tile_at(p, my_tiles, mt, nt)) ++my_tiles; }
     long long seq = 0;
-    const long long my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const long long total_seq = my_tiles * chunks_per_tile;
+    const long long total_seq = (long long)my_tiles * chunks_per_tile;
     auto issue_res_load = [&](long long sq) {
       const int t = (int)(sq / chunks_per_tile), c = (int)(sq - (long long)t * chunks_per_tile);
-      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int buf = (int)(sq & 1);
+      int mt, nt;
+      tile_at(p, t, mt, nt);
+      const int buf = (int)(sq % nres);
       mbar_expect_tx(&res_full[buf], TC_EPI_TILE);
       tma_load_2d(sRes + buf * TC_EPI_TILE, &tmRes, nt * p.BN + c * 32, mt * TC_BM, &res_full[buf]);
     };
     if (p.tma_epi && has_res && elected) {
-      if (total_seq > 0) issue_res_load(0);
-      if (total_seq > 1) issue_res_load(1);
+      for (int q = 0; q < nres && q < total_seq; ++q) issue_res_load(q);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+    int m_tile, n_tile;
+    for (int it = 0; tile_at(p, it, m_tile, n_tile); ++it) {
       const long long m = (long long)m_tile * TC_BM + row_in_tile;
       const bool valid = m < p.M;
       int img = 0, y = 0, x = 0;
@@ -332,7 +361,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (p.tma_epi) {
         const uint32_t sw = (uint32_t)((row_in_tile >> 1) & 3);      // SWIZZLE_64B: 16B chunk index ^= address bits [7,8]
         for (int c = 0; c < chunks_per_tile; ++c, ++seq) {
-          const int buf = (int)(seq & 1);
+          const int obuf = (int)(seq & 1);
           uint32_t r[32];
           tmem_ld32(t_base + c * 32, r);
           tmem_ld_wait();
@@ -345,8 +374,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             v[i + 2] = __uint_as_float(r[i + 2]) + b.z; v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
           }
           if (has_res) {
-            mbar_wait(&res_full[buf], (uint32_t)((seq >> 1) & 1));
-            const uint8_t* rrow = sRes + buf * TC_EPI_TILE + row_in_tile * 64;
+            const int rbuf = (int)(seq % nres);
+            mbar_wait(&res_full[rbuf], (uint32_t)((seq / nres) & 1));
+            const uint8_t* rrow = sRes + rbuf * TC_EPI_TILE + row_in_tile * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 rv = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)j ^ sw) << 4));
@@ -366,10 +396,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
-          // the store issued from sOut[buf] two chunks ago must have finished reading smem
+          // the store issued from sOut[obuf] two chunks ago must have finished reading smem
           if (elected) bulk_wait_read<1>();
           epi_barrier();
-          uint8_t* orow = sOut + buf * TC_EPI_TILE + row_in_tile * 64;
+          uint8_t* orow = sOut + obuf * TC_EPI_TILE + row_in_tile * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 pk;
@@ -385,9 +415,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           fence_async_smem();
           epi_barrier();
           if (elected) {
-            tma_store_2d(&tmOut, sOut + buf * TC_EPI_TILE, col, m_tile * TC_BM);
+            tma_store_2d(&tmOut, sOut + obuf * TC_EPI_TILE, col, m_tile * TC_BM);
             bulk_commit();
-            if (has_res && seq + 2 < total_seq) issue_res_load(seq + 2);     // sRes[buf] was consumed before the barrier
+            if (has_res && seq + nres < total_seq) issue_res_load(seq + nres);   // its sRes buffer was consumed before the barrier
           }
         }
       } else {
@@ -477,13 +507,28 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   while (cols < 2 * pl->BN) cols <<= 1;
   pl->tmem_cols = cols;
   pl->tma_epi = (a.out_mode == 0 && pl->BN % 32 == 0) ? 1 : 0;
-  const size_t per_stage = TC_A_STAGE + (size_t)pl->BN * TC_BK * 2;
-  const size_t epi_bytes = pl->tma_epi ? 4 * TC_EPI_TILE : 0;
-  const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + epi_bytes;
-  int stages = (int)((227 * 1024 - fixed) / per_stage);
-  if (stages > 8) stages = 8;
-  pl->stages = stages;
-  pl->smem_bytes = (size_t)stages * per_stage + fixed;
+  const size_t b_stage = (size_t)pl->BN * TC_BK * 2;
+  const int num_kb = a.ntaps * a.Cin / TC_BK;
+  const size_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  pl->nres = (pl->tma_epi && a.residual) ? 4 : 0;
+  size_t epi_bytes = pl->tma_epi ? (size_t)(2 + pl->nres) * TC_EPI_TILE : 0;
+  // weight-resident mode: the whole [BN x Ktot] slice fits next to >= 3 A stages
+  pl->b_resident = 0;
+  pl->grid_mult = 1;
+  const int n_tiles = a.Cout_pad / pl->BN;
+  if (!getenv("YOLACT_B200_NO_BRES") && (size_t)num_kb * b_stage + epi_bytes + 3 * TC_A_STAGE <= budget && n_tiles <= 64) {
+    pl->b_resident = 1;
+    pl->grid_mult = n_tiles;
+    int stages = (int)((budget - epi_bytes - (size_t)num_kb * b_stage) / TC_A_STAGE);
+    pl->stages = stages > 8 ? 8 : stages;
+    pl->smem_bytes = (size_t)pl->stages * TC_A_STAGE + (size_t)num_kb * b_stage + epi_bytes + 1024 + 512;
+  } else {
+    const size_t per_stage = TC_A_STAGE + b_stage;
+    if (epi_bytes + 3 * per_stage > budget && pl->nres > 2) { pl->nres = 2; epi_bytes = (size_t)(2 + pl->nres) * TC_EPI_TILE; }
+    int stages = (int)((budget - epi_bytes) / per_stage);
+    pl->stages = stages > 8 ? 8 : stages;
+    pl->smem_bytes = (size_t)pl->stages * per_stage + epi_bytes + 1024 + 512;
+  }
   const int Ktot = a.ntaps * a.Cin;
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
@@ -516,11 +561,16 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
-  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi;
+  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sms ? total : sms;
+  int grid = total < sms ? total : sms;
+  if (pl->b_resident) {
+    grid = sms / p.n_tiles * p.n_tiles;                       // whole groups of N tiles
+    if (grid > total) grid = total;                           // total is a multiple of n_tiles
+    if (grid < p.n_tiles) grid = p.n_tiles;
+  }
   k_conv_tc<<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
   YB_CHECK_LAUNCH();
   return YB_OK;
