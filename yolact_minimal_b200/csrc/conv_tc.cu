@@ -9,7 +9,7 @@
 //               tile, both 128B-swizzled, into a ring of shared-memory stages (mbarrier full/empty)
 //   warp 1      allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16) from one elected lane,
 //               tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2..5  epilogue: tcgen05.ld the 128xBN fp32 accumulator (double-buffered in TMEM so the
+//   warps 2..9  epilogue (two groups of four warps, alternating 32-column chunks): tcgen05.ld the 128xBN fp32 accumulator (double-buffered in TMEM so the
 //               next tile's MMAs overlap), + folded-BN bias, + residual, ReLU, halo zeroing,
 //               bf16 (or dense fp32) stores
 // Tiles are scheduled round-robin over the persistent grid, N-tiles of one M-tile adjacent so
@@ -25,7 +25,9 @@ namespace yb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;             // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int TC_OUT_BUFS = 2;                // output staging buffers per epilogue warp
+constexpr uint32_t TC_WARP_TILE = 32 * 32 * 2;  // 2 KiB: one warp's 32 rows x 32 columns of 16-bit outputs
 constexpr uint32_t TC_A_STAGE = TC_BM * TC_BK * 2;   // 16 KiB
 constexpr uint32_t TC_EPI_TILE = TC_BM * 32 * 2;     // 8 KiB: 128 rows x 32 columns of 16-bit outputs
 
@@ -91,7 +93,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -145,6 +147,12 @@ template <bool F16> __device__ __forceinline__ uint32_t pack2(float a, float b) 
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+}
+// no saturation (callers clamp when needed)
+template <bool F16> __device__ __forceinline__ uint32_t pack2_raw(float a, float b) {
+  if (F16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 template <bool F16> __device__ __forceinline__ float2 unpack2(uint32_t u) {
   if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
@@ -222,6 +230,7 @@ __device__ __forceinline__ bool tile_at(const TcParams& p, int i, int& m_tile, i
   return true;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcParams p) {
@@ -231,14 +240,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int num_kb = p.ntaps * p.kb_per_tap;
   uint8_t* sA = smem;                                                               // [stages][16 KiB]
   uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;                               // [stages | num_kb][BN x 128 B]
-  uint8_t* sOut = sB + (size_t)(p.b_resident ? num_kb : p.stages) * b_stage;        // [2][128 rows x 64 B], SWIZZLE_64B
-  uint8_t* sRes = sOut + (p.tma_epi ? 2 * TC_EPI_TILE : 0);                         // [nres][128 rows x 64 B]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (size_t)p.nres * TC_EPI_TILE);
+  uint8_t* sOut = sB + (size_t)(p.b_resident ? num_kb : p.stages) * b_stage;        // [8 warps][2][32 rows x 64 B], SWIZZLE_64B
+  uint8_t* sRes = sOut + (p.tma_epi ? 8 * TC_OUT_BUFS * TC_WARP_TILE : 0);          // [8 warps][nres][32 rows x 64 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (size_t)8 * p.nres * TC_WARP_TILE);
   uint64_t* empty = full + 8;
   uint64_t* tmem_full = empty + 8;             // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint64_t* res_full = tmem_empty + 2;         // [8]
-  uint64_t* b_full = res_full + 8;             // [1]
+  uint64_t* res_full = tmem_empty + 2;         // [8 warps][4]
+  uint64_t* b_full = res_full + 32;            // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -246,8 +255,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&res_full[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 32; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -289,7 +299,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ================= MMA issuer =================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16 (1) or f16 (0), K-major both, N=BN, M=128
-      const uint32_t fmt = p.is_f16 ? 0u : 1u;
+      const uint32_t fmt = F16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -317,29 +327,38 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
+    // ================= epilogue: 8 independent warps =================
+    // Warp (grp, quad) owns rows quad*32..+31 (its TMEM lane quadrant) of the 32-column chunks
+    // c == grp (mod 2) of every tile, with private smem staging, mbarriers and bulk-async groups:
+    // TMEM -> registers -> (+bias, +residual tile prefetched by TMA, ReLU, halo) -> smem -> TMA store,
+    // no block-level synchronisation anywhere in the epilogue.
+    const int grp = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
-    const bool elected = threadIdx.x == 64;                      // warp 2, lane 0
+    const int wslot = warp - 2;                                      // 0..7: private staging buffers / barriers per warp
+    const bool elected = lane == 0;
     const bool has_res = p.residual != nullptr;
-    const int chunks_per_tile = p.BN / 32;
-    const int nres = p.nres;
+    const int chunks_per_tile = (p.BN + 31) / 32;
+    const int my_chunks = (chunks_per_tile - grp + 1) / 2;            // chunks grp, grp+2, ...
+    const int nres = p.nres;                                         // residual buffers per warp (power of two)
+    const int nres_shift = nres == 4 ? 2 : (nres == 2 ? 1 : 0);
+    uint8_t* gOut = sOut + wslot * (TC_OUT_BUFS * TC_WARP_TILE);
+    uint8_t* gRes = sRes + wslot * (nres * TC_WARP_TILE);
+    uint64_t* gres_full = res_full + wslot * 4;
     int acc = 0; uint32_t acc_phase = 0;
-    // running chunk sequence over all tiles of this CTA (TMA epilogue): seq -> (local tile index, chunk)
-    int my_tiles = 0;
-    { int mt, nt; while (tile_at(p, my_tiles, mt, nt)) ++my_tiles; }
-    long long seq = 0;
-    const long long total_seq = (long long)my_tiles * chunks_per_tile;
-    auto issue_res_load = [&](long long sq) {
-      const int t = (int)(sq / chunks_per_tile), c = (int)(sq - (long long)t * chunks_per_tile);
-      int mt, nt;
-      tile_at(p, t, mt, nt);
-      const int buf = (int)(sq % nres);
-      mbar_expect_tx(&res_full[buf], TC_EPI_TILE);
-      tma_load_2d(sRes + buf * TC_EPI_TILE, &tmRes, nt * p.BN + c * 32, mt * TC_BM, &res_full[buf]);
+    int seq = 0;                                                     // warp-local chunk sequence over all tiles
+    // residual prefetch cursor: next (tile iteration, local chunk) to request
+    int pf_it = 0, pf_j = 0, pf_seq = 0, pf_mt = 0, pf_nt = 0;
+    bool pf_ok = p.tma_epi && has_res && my_chunks > 0 && tile_at(p, 0, pf_mt, pf_nt);
+    auto issue_res_load = [&]() {
+      const int buf = pf_seq & (nres - 1);
+      mbar_expect_tx(&gres_full[buf], TC_WARP_TILE);
+      tma_load_2d(gRes + buf * TC_WARP_TILE, &tmRes, pf_nt * p.BN + (2 * pf_j + grp) * 32, pf_mt * TC_BM + quad * 32, &gres_full[buf]);
+      ++pf_seq;
+      if (++pf_j == my_chunks) { pf_j = 0; ++pf_it; pf_ok = tile_at(p, pf_it, pf_mt, pf_nt); }
     };
-    if (p.tma_epi && has_res && elected) {
-      for (int q = 0; q < nres && q < total_seq; ++q) issue_res_load(q);
+    if (elected) {
+      for (int q = 0; q < nres && pf_ok; ++q) issue_res_load();
     }
     int m_tile, n_tile;
     for (int it = 0; tile_at(p, it, m_tile, n_tile); ++it) {
@@ -359,80 +378,77 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
       const int n0 = n_tile * p.BN;
       if (p.tma_epi) {
-        const uint32_t sw = (uint32_t)((row_in_tile >> 1) & 3);      // SWIZZLE_64B: 16B chunk index ^= address bits [7,8]
-        for (int c = 0; c < chunks_per_tile; ++c, ++seq) {
-          const int obuf = (int)(seq & 1);
-          uint32_t r[32];
-          tmem_ld32(t_base + c * 32, r);
-          tmem_ld_wait();
-          float v[32];
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);             // SWIZZLE_64B: 16B chunk index ^= address bits [7,8]
+        const bool zero_row = halo || !valid;
+        const int row0 = m_tile * TC_BM + quad * 32;
+        uint32_t r[32];
+        if (my_chunks > 0) tmem_ld32(t_base + grp * 32, r);         // software pipeline: chunk j+1's TMEM load overlaps chunk j
+        for (int j = 0; j < my_chunks; ++j, ++seq) {
+          const int c = 2 * j + grp;
           const int col = n0 + c * 32;
+          const int obuf = seq & (TC_OUT_BUFS - 1);
+          float v[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
-            v[i] = __uint_as_float(r[i]) + b.x; v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
-            v[i + 2] = __uint_as_float(r[i + 2]) + b.z; v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+            v[i] = b.x; v[i + 1] = b.y; v[i + 2] = b.z; v[i + 3] = b.w;
           }
-          if (has_res) {
-            const int rbuf = (int)(seq % nres);
-            mbar_wait(&res_full[rbuf], (uint32_t)((seq / nres) & 1));
-            const uint8_t* rrow = sRes + rbuf * TC_EPI_TILE + row_in_tile * 64;
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)j ^ sw) << 4));
+          for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+          if (j + 1 < my_chunks) tmem_ld32(t_base + (c + 2) * 32, r);
+          if (has_res) {
+            const int rbuf = seq & (nres - 1);
+            mbar_wait(&gres_full[rbuf], (uint32_t)((seq >> nres_shift) & 1));
+            const uint8_t* rrow = gRes + rbuf * TC_WARP_TILE + lane * 64;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)jj ^ sw) << 4));
               const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float2 f = p.is_f16 ? unpack2<true>(rw[q]) : unpack2<false>(rw[q]);
-                v[j * 8 + 2 * q] += f.x; v[j * 8 + 2 * q + 1] += f.y;
+                const float2 f = unpack2<F16>(rw[q]);
+                v[jj * 8 + 2 * q] += f.x; v[jj * 8 + 2 * q + 1] += f.y;
               }
             }
           }
           if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (halo || !valid) {
+            for (int i = 0; i < 32; ++i) v[i] = F16 ? fminf(fmaxf(v[i], 0.f), 65504.f) : fmaxf(v[i], 0.f);
+          } else if (F16) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -65504.f), 65504.f);
           }
-          // the store issued from sOut[obuf] two chunks ago must have finished reading smem
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = zero_row ? 0u : pack2_raw<F16>(v[2 * i], v[2 * i + 1]);
+          // gOut[obuf] was last read by this warp's store of chunk seq-2: retire it before overwriting
           if (elected) bulk_wait_read<1>();
-          epi_barrier();
-          uint8_t* orow = sOut + obuf * TC_EPI_TILE + row_in_tile * 64;
+          __syncwarp();
+          uint8_t* orow = gOut + obuf * TC_WARP_TILE + lane * 64;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            if (p.is_f16) {
-              pk.x = pack2<true>(v[j * 8], v[j * 8 + 1]); pk.y = pack2<true>(v[j * 8 + 2], v[j * 8 + 3]);
-              pk.z = pack2<true>(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack2<true>(v[j * 8 + 6], v[j * 8 + 7]);
-            } else {
-              pk.x = pack2<false>(v[j * 8], v[j * 8 + 1]); pk.y = pack2<false>(v[j * 8 + 2], v[j * 8 + 3]);
-              pk.z = pack2<false>(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack2<false>(v[j * 8 + 6], v[j * 8 + 7]);
-            }
-            *reinterpret_cast<uint4*>(orow + (((uint32_t)j ^ sw) << 4)) = pk;
-          }
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<uint4*>(orow + (((uint32_t)jj ^ sw) << 4)) = make_uint4(pk[jj * 4], pk[jj * 4 + 1], pk[jj * 4 + 2], pk[jj * 4 + 3]);
           fence_async_smem();
-          epi_barrier();
+          __syncwarp();
           if (elected) {
-            tma_store_2d(&tmOut, sOut + obuf * TC_EPI_TILE, col, m_tile * TC_BM);
+            tma_store_2d(&tmOut, gOut + obuf * TC_WARP_TILE, col, row0);
             bulk_commit();
-            if (has_res && seq + nres < total_seq) issue_res_load(seq + nres);   // its sRes buffer was consumed before the barrier
+            if (pf_ok) issue_res_load();                         // the buffer of chunk seq was consumed before the __syncwarp
           }
         }
       } else {
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        // direct-store path (dense fp32 outputs / odd tile widths): group g takes chunks c == g (mod 2)
+        for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
           uint32_t r[32];
           if (c0 + 32 <= p.BN) {
             tmem_ld32(t_base + c0, r);
             tmem_ld_wait();
-            if (p.is_f16) epilogue_chunk<32, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
-            else epilogue_chunk<32, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
+            epilogue_chunk<32, F16>(p, r, m, n0 + c0, valid, halo, img, y, x);
           } else {
             tmem_ld16(t_base + c0, r);
             tmem_ld_wait();
-            if (p.is_f16) epilogue_chunk<16, true>(p, r, m, n0 + c0, valid, halo, img, y, x);
-            else epilogue_chunk<16, false>(p, r, m, n0 + c0, valid, halo, img, y, x);
+            epilogue_chunk<16, F16>(p, r, m, n0 + c0, valid, halo, img, y, x);
           }
         }
       }
@@ -509,9 +525,10 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   pl->tma_epi = (a.out_mode == 0 && pl->BN % 32 == 0) ? 1 : 0;
   const size_t b_stage = (size_t)pl->BN * TC_BK * 2;
   const int num_kb = a.ntaps * a.Cin / TC_BK;
-  const size_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
-  pl->nres = (pl->tma_epi && a.residual) ? 4 : 0;
-  size_t epi_bytes = pl->tma_epi ? (size_t)(2 + pl->nres) * TC_EPI_TILE : 0;
+  const size_t budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers*/;
+  pl->nres = (pl->tma_epi && a.residual) ? 2 : 0;                  // residual buffers per epilogue group
+  if (pl->nres) if (const char* e = getenv("YOLACT_B200_NRES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) pl->nres = v; }
+  size_t epi_bytes = pl->tma_epi ? (size_t)8 * (TC_OUT_BUFS + pl->nres) * TC_WARP_TILE : 0;
   // weight-resident mode: the whole [BN x Ktot] slice fits next to >= 3 A stages
   pl->b_resident = 0;
   pl->grid_mult = 1;
@@ -521,13 +538,12 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
     pl->grid_mult = n_tiles;
     int stages = (int)((budget - epi_bytes - (size_t)num_kb * b_stage) / TC_A_STAGE);
     pl->stages = stages > 8 ? 8 : stages;
-    pl->smem_bytes = (size_t)pl->stages * TC_A_STAGE + (size_t)num_kb * b_stage + epi_bytes + 1024 + 512;
+    pl->smem_bytes = (size_t)pl->stages * TC_A_STAGE + (size_t)num_kb * b_stage + epi_bytes + 1024 + 1024;
   } else {
     const size_t per_stage = TC_A_STAGE + b_stage;
-    if (epi_bytes + 3 * per_stage > budget && pl->nres > 2) { pl->nres = 2; epi_bytes = (size_t)(2 + pl->nres) * TC_EPI_TILE; }
     int stages = (int)((budget - epi_bytes) / per_stage);
     pl->stages = stages > 8 ? 8 : stages;
-    pl->smem_bytes = (size_t)pl->stages * per_stage + epi_bytes + 1024 + 512;
+    pl->smem_bytes = (size_t)pl->stages * per_stage + epi_bytes + 1024 + 1024;
   }
   const int Ktot = a.ntaps * a.Cin;
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
@@ -537,13 +553,16 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;                      // placeholders when the TMA epilogue is off
   if (s == YB_OK && pl->tma_epi) {
     const uint64_t out_rows = (uint64_t)max_batch * a.g.plane();
-    s = make_map(&pl->tmOut, a.out, (uint64_t)a.Cout, out_rows, TC_BM, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (s == YB_OK && a.residual) s = make_map(&pl->tmRes, a.residual, (uint64_t)a.Cout, out_rows, TC_BM, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    s = make_map(&pl->tmOut, a.out, (uint64_t)a.Cout, out_rows, 32, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (s == YB_OK && a.residual) s = make_map(&pl->tmRes, a.residual, (uint64_t)a.Cout, out_rows, 32, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   }
   if (s != YB_OK) { delete pl; return s; }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
   if (attr_err != cudaSuccess) { delete pl; set_error("cudaFuncSetAttribute(k_conv_tc) failed: %s", cudaGetErrorString(attr_err)); return YB_ERR_CUDA; }
   *out = pl;
   return YB_OK;
@@ -571,7 +590,8 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
     if (grid > total) grid = total;                           // total is a multiple of n_tiles
     if (grid < p.n_tiles) grid = p.n_tiles;
   }
-  k_conv_tc<<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
+  if (p.is_f16) k_conv_tc<true><<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
+  else k_conv_tc<false><<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }

@@ -793,7 +793,24 @@ extern "C" int yb_conv2d(const float* x, int batch, int cin, int h, const float*
     YB_REQUIRE(tc_supported(a), YB_ERR_UNSUPPORTED, "yb_conv2d: shape/precision not supported by the tcgen05 kernel");
     TcPlan* pl = nullptr;
     YB_PROPAGATE(tc_plan_create(a, batch, &pl));
-    const int st = launch_conv_tc(pl, a, nullptr);
+    int st = launch_conv_tc(pl, a, nullptr);
+    if (const char* reps_env = getenv("YOLACT_B200_CONV_REPS")) {        // tooling: time repeated launches with CUDA events
+      const int reps = atoi(reps_env);
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0, nullptr);
+      for (int i = 0; i < reps && st == YB_OK; ++i) st = launch_conv_tc(pl, a, nullptr);
+      cudaEventRecord(e1, nullptr);
+      cudaEventSynchronize(e1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double us = 1e3 * ms / (reps > 0 ? reps : 1);
+      const double flops = 2.0 * batch * ho * ho * (double)cout * cin * k2;
+      fprintf(stderr, "[yb_conv2d] B=%d Cin=%d H=%d Cout=%d k=%d s=%d res=%d: %.1f us/launch, %.0f TFLOP/s\n", batch, cin, h, cout, k,
+              stride, residual ? 1 : 0, us, flops / us * 1e-6);
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     tc_plan_destroy(pl);
     YB_PROPAGATE(st);

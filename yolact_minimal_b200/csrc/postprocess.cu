@@ -183,9 +183,15 @@ __device__ SelectResult block_select_kth_largest(int n, int kk, F value, int* hi
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += nt) hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-      uint32_t v;
-      if (value(i, v) && (v & mask) == desired) atomicAdd(&hist[(v >> shift) & 255u], 1);
+    // warp-aggregated histogram: lanes that hit the same bin elect one leader (scores cluster in a
+    // few exponent bins, so naive shared atomics would serialise 32-way)
+    const int n_round = (n + 31) & ~31;
+    for (int i = tid; i < n_round; i += nt) {
+      uint32_t v = 0;
+      const bool ok = i < n && value(i, v) && (v & mask) == desired;
+      const uint32_t bin = ok ? ((v >> shift) & 255u) : 0xFFFFFFFFu;
+      const unsigned peers = __match_any_sync(kFull, bin);
+      if (ok && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
     }
     __syncthreads();
     if (tid < 32) {
@@ -252,6 +258,7 @@ k_class_fast_nms(int A, int C1, int top_k, float iou_thr, int smem_keys, DetectW
   __shared__ int s_tmp[4];
   __shared__ int s_cnt;
   __shared__ int s_wcnt[kThreads / 32];
+  __shared__ int s_keep[kSortCap];
 
   const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int n = ws.cand_count[b];
@@ -304,13 +311,19 @@ k_class_fast_nms(int A, int C1, int top_k, float iou_thr, int smem_keys, DetectW
   __syncthreads();
 
   // keep_j = (0 <= thr) && all_{i<j} IoU(i,j) <= thr   (NaN compares false -> dropped;
-  // the triu'd matrix contributes the 0 -- output_utils.py:21-26)
-  bool keep = false;
-  if (tid < k) {
-    keep = 0.f <= iou_thr;
-    const float4 bj = s_box[tid];
-    for (int i = 0; i < tid && keep; ++i) keep = iou_exact(s_box[i], bj) <= iou_thr;
+  // the triu'd matrix contributes the 0 -- output_utils.py:21-26).  The k(k-1)/2 pairs are spread
+  // over the block.
+  if (tid < kSortCap) s_keep[tid] = (tid < k && 0.f <= iou_thr) ? 1 : 0;
+  __syncthreads();
+  for (int idx = tid; idx < k * 4; idx += kThreads) {          // 4 threads per column j, rows interleaved
+    const int sub = idx & 3, j = idx >> 2;
+    const float4 bj = s_box[j];
+    bool ok = true;
+    for (int i = sub; i < j && ok; i += 4) ok = iou_exact(s_box[i], bj) <= iou_thr;
+    if (!ok) s_keep[j] = 0;
   }
+  __syncthreads();
+  const bool keep = tid < k && s_keep[tid] != 0;
   const unsigned bal = __ballot_sync(kFull, keep);
   const int w = tid >> 5, lane = tid & 31;
   if (lane == 0) s_wcnt[w] = __popc(bal);
