@@ -77,3 +77,26 @@ def test_forward_golden_small(key):
     assert cls.shape[1] == int(g[key + '/shapes'][0]) and proto.shape[1] == int(g[key + '/shapes'][1])
     for mine, name in ((cls[:, ::sub], 'cls'), (box[:, ::sub], 'box'), (coef[:, ::sub], 'coef'), (proto[:, ::sub, ::sub], 'proto')):
         assert np.allclose(mine, g[f'{key}/{name}'], rtol=0, atol=2e-6), name
+
+
+def test_c_hard_nms_matches_numpy_oracle_and_golden():
+    """oracle/hard_nms.c (plain-C restatement of cython_nms.pyx) == numpy oracle == reference goldens."""
+    import ctypes, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(['make', '-s', '-C', os.path.join(root, 'oracle')])
+    lib = ctypes.CDLL(os.path.join(root, 'oracle', '_build', 'liboracle_hard_nms.so'))
+    lib.oracle_hard_nms.restype = ctypes.c_int
+    lib.oracle_hard_nms.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p]
+    g = load_golden('hard_nms.npz')
+    for seed, n in ((1, 1), (2, 17), (3, 300), (4, 1500)):
+        xy = synth.uniform(seed, 11, (n, 2)) * 400
+        wh = synth.uniform(seed, 12, (n, 2)) * 120 + 1
+        sc = synth.uniform(seed, 13, (n, 1))
+        dets = np.ascontiguousarray(np.concatenate([xy, xy + wh, sc], 1).astype(np.float32))
+        for thr in (0.3, 0.5):
+            keep = np.zeros(n, np.uint8)
+            kept = lib.oracle_hard_nms(dets.ctypes.data, n, thr, keep.ctypes.data)
+            idx = np.nonzero(keep)[0]
+            assert kept == len(idx)
+            assert np.array_equal(idx, g[f's{seed}_n{n}_t{thr}'])
+            assert np.array_equal(idx, pp.hard_nms(dets, thr))
