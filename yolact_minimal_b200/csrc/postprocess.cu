@@ -183,15 +183,9 @@ __device__ SelectResult block_select_kth_largest(int n, int kk, F value, int* hi
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += nt) hist[i] = 0;
     __syncthreads();
-    // warp-aggregated histogram: lanes that hit the same bin elect one leader (scores cluster in a
-    // few exponent bins, so naive shared atomics would serialise 32-way)
-    const int n_round = (n + 31) & ~31;
-    for (int i = tid; i < n_round; i += nt) {
-      uint32_t v = 0;
-      const bool ok = i < n && value(i, v) && (v & mask) == desired;
-      const uint32_t bin = ok ? ((v >> shift) & 255u) : 0xFFFFFFFFu;
-      const unsigned peers = __match_any_sync(kFull, bin);
-      if (ok && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    for (int i = tid; i < n; i += nt) {
+      uint32_t v;
+      if (value(i, v) && (v & mask) == desired) atomicAdd(&hist[(v >> shift) & 255u], 1);
     }
     __syncthreads();
     if (tid < 32) {
@@ -247,85 +241,162 @@ __device__ void bitonic_sort_256(unsigned long long* key, int* val) {
 
 // --------------------------------------------------------------------------------------------
 // phase 2 (Fast-NMS): one block per (class, image)   utils/output_utils.py:11-31
+//   stage 1  cut the class row (up to A scores) down to a compact candidate list in shared memory:
+//            a 256-element sample is sorted, its j-th largest value is a threshold that keeps
+//            ~4*top_k elements in expectation; one streaming pass compacts the survivors
+//            (ballot + one shared atomic per warp).  If fewer than top_k or more than kCompactCap
+//            survive (probability < 1e-3) the exact selection simply runs over the whole row.
+//   stage 2  exact top_k of the compact list: 8-bit radix select, tie-break on anchor index,
+//            bitonic sort of the <= 256 winners by (score desc, anchor asc)
+//   stage 3  k x k IoU upper triangle, keep rule, ordered compaction of the survivors
 // --------------------------------------------------------------------------------------------
+constexpr int kCompactCap = 4096;
+
+__device__ void bitonic_sort_256_desc_u32(uint32_t* key) {
+  const int tid = threadIdx.x;
+  for (int size = 2; size <= 256; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      const int p = tid ^ stride;
+      if (p > tid) {
+        const bool desc = (tid & size) == 0;
+        const uint32_t a = key[tid], b = key[p];
+        if ((a < b) == desc) { key[tid] = b; key[p] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// IoU(a,b) <= thr with the reference's fp32 rounding (utils/box_utils.py:28-36): a 2-instruction
+// reciprocal estimate decides unless it lands within 4e-6 of the threshold, where the exactly
+// rounded division is used (also covers NaN: 0/0 falls through to the exact path and compares false).
+__device__ __forceinline__ bool iou_le(float4 a, float area_a, float4 b, float area_b, float thr) {
+  float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  w = w < 0.f ? 0.f : w;
+  h = h < 0.f ? 0.f : h;
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  const float q = inter * __frcp_rn(uni);
+  if (fabsf(q - thr) > 4e-6f) return q <= thr;
+  return __fdiv_rn(inter, uni) <= thr;
+}
+
 __global__ void __launch_bounds__(kThreads)
-k_class_fast_nms(int A, int C1, int top_k, float iou_thr, int smem_keys, DetectWs ws) {
-  extern __shared__ uint32_t s_keys[];             // [smem_keys] ordered score keys (0 if unused)
+k_class_fast_nms(int A, int C1, int top_k, float iou_thr, DetectWs ws) {
+  __shared__ uint32_t s_ckey[kCompactCap];         // compact candidates: ordered score keys
+  __shared__ int s_cidx[kCompactCap];              //                    : slot in the candidate list
+  __shared__ uint32_t s_sample[256];
   __shared__ unsigned long long s_sort[kSortCap];
   __shared__ int s_slot[kSortCap];
   __shared__ float4 s_box[kSortCap];
+  __shared__ float s_area[kSortCap];
   __shared__ int s_hist[256];
   __shared__ int s_tmp[4];
-  __shared__ int s_cnt;
+  __shared__ int s_cnt, s_m;
   __shared__ int s_wcnt[kThreads / 32];
   __shared__ int s_keep[kSortCap];
 
-  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int n = ws.cand_count[b];
   int* out_cnt = ws.cls_cnt + (size_t)b * C1 + c;
   if (n == 0) { if (tid == 0) *out_cnt = 0; return; }
   const int k = min(top_k, n);
   const float* row = ws.scoreT + ((size_t)b * C1 + c) * A;
   const int* canchor = ws.cand_anchor + (size_t)b * A;
-  const bool in_smem = n <= smem_keys;
-  if (in_smem) {
-    for (int i = tid; i < n; i += kThreads) s_keys[i] = float_to_ordered(row[i]);
-  }
-  if (tid == 0) s_cnt = 0;
-  __syncthreads();
-  auto key_of = [&](int i) -> uint32_t { return in_smem ? s_keys[i] : float_to_ordered(row[i]); };
+  if (tid == 0) { s_cnt = 0; s_m = 0; }
 
-  if (n > k) {
-    SelectResult r = block_select_kth_largest(n, k, [&](int i, uint32_t& v) { v = key_of(i); return true; }, s_hist, s_tmp);
+  // ---- stage 1: compact candidate list ---------------------------------------------------------
+  bool full_scan = false;                          // exact selection over the whole row (rare)
+  int m = n;
+  if (n <= kCompactCap) {
+    for (int i = tid; i < n; i += kThreads) { s_ckey[i] = float_to_ordered(row[i]); s_cidx[i] = i; }
+    __syncthreads();
+  } else {
+    const int stride = n / 256;
+    s_sample[tid] = float_to_ordered(row[tid * stride]);
+    bitonic_sort_256_desc_u32(s_sample);
+    int j = (int)(((long long)256 * 4 * k + n - 1) / n) + 4;        // expected survivors ~ 4k + 4n/256
+    if (j > 255) j = 255;
+    const uint32_t cut = s_sample[j];
+    const int n_round = (n + 31) & ~31;
+    for (int i = tid; i < n_round; i += kThreads) {
+      const uint32_t key = i < n ? float_to_ordered(row[i]) : 0u;
+      const bool take = i < n && key >= cut;
+      const unsigned bal = __ballot_sync(kFull, take);
+      int base = 0;
+      if (lane == 0 && bal) base = atomicAdd(&s_m, __popc(bal));
+      base = __shfl_sync(kFull, base, 0);
+      if (take) {
+        const int pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (pos < kCompactCap) { s_ckey[pos] = key; s_cidx[pos] = i; }
+      }
+    }
+    __syncthreads();
+    m = s_m;
+    if (m < k || m > kCompactCap) { full_scan = true; m = n; }
+  }
+  auto key_of = [&](int i) -> uint32_t { return full_scan ? float_to_ordered(row[i]) : s_ckey[i]; };
+  auto slot_of = [&](int i) -> int { return full_scan ? i : s_cidx[i]; };
+
+  // ---- stage 2: exact top-k by (score desc, anchor asc) ----------------------------------------
+  if (m > k) {
+    SelectResult r = block_select_kth_largest(m, k, [&](int i, uint32_t& v) { v = key_of(i); return true; }, s_hist, s_tmp);
     uint32_t anchor_max = 0xFFFFFFFFu;   // take ties with anchor <= anchor_max
     if (r.cnt_eq > r.need_eq) {
       // exact score ties at the cut: the reference's stable sort keeps the lowest candidate
       // indices (== lowest anchors).  Select the need_eq smallest anchors among the ties.
       const uint32_t T = r.thresh;
       SelectResult r2 = block_select_kth_largest(
-          n, r.need_eq, [&](int i, uint32_t& v) { v = ~(uint32_t)canchor[i]; return key_of(i) == T; }, s_hist, s_tmp);
+          m, r.need_eq, [&](int i, uint32_t& v) { v = ~(uint32_t)canchor[slot_of(i)]; return key_of(i) == T; }, s_hist, s_tmp);
       anchor_max = ~r2.thresh;
     }
-    for (int i = tid; i < n; i += kThreads) {
+    for (int i = tid; i < m; i += kThreads) {
       const uint32_t key = key_of(i);
-      if (key > r.thresh || (key == r.thresh && (uint32_t)canchor[i] <= anchor_max)) {
-        const int pos = atomicAdd(&s_cnt, 1);
-        if (pos < kSortCap) {
-          s_sort[pos] = ((unsigned long long)(~key) << 32) | (uint32_t)canchor[i];
-          s_slot[pos] = i;
+      if (key >= r.thresh) {
+        const int slot = slot_of(i);
+        const uint32_t anc = (uint32_t)canchor[slot];
+        if (key > r.thresh || anc <= anchor_max) {
+          const int pos = atomicAdd(&s_cnt, 1);
+          if (pos < kSortCap) { s_sort[pos] = ((unsigned long long)(~key) << 32) | anc; s_slot[pos] = slot; }
         }
       }
     }
   } else {
-    for (int i = tid; i < n; i += kThreads) {
-      s_sort[i] = ((unsigned long long)(~key_of(i)) << 32) | (uint32_t)canchor[i];
-      s_slot[i] = i;
+    for (int i = tid; i < m; i += kThreads) {
+      const int slot = slot_of(i);
+      s_sort[i] = ((unsigned long long)(~key_of(i)) << 32) | (uint32_t)canchor[slot];
+      s_slot[i] = slot;
     }
   }
   __syncthreads();
   for (int i = k + tid; i < kSortCap; i += kThreads) { s_sort[i] = ~0ull; s_slot[i] = -1; }
   bitonic_sort_256(s_sort, s_slot);
 
+  // ---- stage 3: Fast-NMS keep rule ----------------------------------------------------------------
   const float4* cbox = ws.cand_box + (size_t)b * A;
-  if (tid < k) s_box[tid] = cbox[s_slot[tid]];
-  __syncthreads();
-
+  if (tid < k) {
+    const float4 bx = cbox[s_slot[tid]];
+    s_box[tid] = bx;
+    s_area[tid] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+  }
   // keep_j = (0 <= thr) && all_{i<j} IoU(i,j) <= thr   (NaN compares false -> dropped;
-  // the triu'd matrix contributes the 0 -- output_utils.py:21-26).  The k(k-1)/2 pairs are spread
-  // over the block.
+  // the triu'd matrix contributes the 0 -- output_utils.py:21-26).
   if (tid < kSortCap) s_keep[tid] = (tid < k && 0.f <= iou_thr) ? 1 : 0;
   __syncthreads();
   for (int idx = tid; idx < k * 4; idx += kThreads) {          // 4 threads per column j, rows interleaved
     const int sub = idx & 3, j = idx >> 2;
     const float4 bj = s_box[j];
+    const float aj = s_area[j];
     bool ok = true;
-    for (int i = sub; i < j && ok; i += 4) ok = iou_exact(s_box[i], bj) <= iou_thr;
+    for (int i = sub; i < j && ok; i += 4) ok = iou_le(s_box[i], s_area[i], bj, aj, iou_thr);
     if (!ok) s_keep[j] = 0;
   }
   __syncthreads();
   const bool keep = tid < k && s_keep[tid] != 0;
   const unsigned bal = __ballot_sync(kFull, keep);
-  const int w = tid >> 5, lane = tid & 31;
+  const int w = tid >> 5;
   if (lane == 0) s_wcnt[w] = __popc(bal);
   __syncthreads();
   int off = 0, tot = 0;
@@ -613,10 +684,7 @@ extern "C" int yb_detect(const float* cls, const float* box, const float* coef, 
     YB_CHECK_LAUNCH();
   }
   if (!p->traditional) {
-    int smem_keys = A <= 40960 ? A : 40960;
-    const size_t smem = (size_t)smem_keys * sizeof(uint32_t);
-    YB_CHECK_CUDA(cudaFuncSetAttribute(k_class_fast_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_class_fast_nms<<<dim3(C1, B), kThreads, smem, stream>>>(A, C1, p->top_k, p->iou_thr, smem_keys, ws);
+    k_class_fast_nms<<<dim3(C1, B), kThreads, 0, stream>>>(A, C1, p->top_k, p->iou_thr, ws);
     YB_CHECK_LAUNCH();
   } else {
     YB_REQUIRE(A <= 49152, YB_ERR_UNSUPPORTED, "yb_detect(traditional): num_anchors=%d > 49152", A);
