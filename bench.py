@@ -258,6 +258,9 @@ def run_ours(args):
            'd2h_bytes_per_step': BATCH * (4 + D * (4 + 4 + 4 + 16 + 128)), 'api': 'yb_net_detect_host (pinned host input)'}
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     # ---- parity gate printed with the number (oracle on a 1-image slice) --------------------------------
     with torch.no_grad():
@@ -307,7 +310,10 @@ def run_ours(args):
                              'sample': f'8 reps x 4 images ({cpu_s:.1f} s): torch fp32 CPU forward + numpy nms()',
                              'fast_nms_us_per_img': cpu_nms_us},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_fp32_oracle_max_abs_err': parity}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
