@@ -218,7 +218,8 @@ def patch_fpn(ryolact):
 def gen_forward(rcfg, ryolact):
     out = {}
     cases = [('res50', 64, 2, 1, False), ('res101', 64, 1, 1, False), ('res50', 128, 2, 4, False),
-             ('res50', 400, 1, 16, True), ('res101', 544, 1, 32, False), ('res101', 550, 1, 32, True)]
+             ('res50', 400, 1, 16, True), ('res101', 544, 1, 32, False), ('res101', 550, 1, 32, True),
+             ('swin_tiny', 96, 2, 1, False), ('swin_tiny', 224, 1, 8, False), ('swin_tiny', 550, 1, 32, True)]
     for arch, S, B, sub, need_patch in cases:
         cfg = ref_cfg(rcfg, arch + '_coco', S)
         sd = ft.synth_state_dict(arch, seed=0)
@@ -233,7 +234,7 @@ def gen_forward(rcfg, ryolact):
             ryolact.FPN.forward = orig
         mine = ft.forward(img, sd, arch)
         errs = [float((a - b).abs().max()) for a, b in zip(ref, mine)]
-        assert max(errs) < 2e-6, (arch, S, errs)
+        assert max(errs) < (2e-5 if arch == 'swin_tiny' else 2e-6), (arch, S, errs)
         key = f'{arch}_S{S}_B{B}'
         cls, box, coef, proto = [t.numpy() for t in ref]
         out[key + '/sub'] = np.int64(sub)

@@ -26,6 +26,10 @@ SHAPES = [
     (2, 256, 5, 256, 3, 2, 1, 0),
     (3, 1024, 35, 256, 1, 1, 1, 0),
     (4, 256, 138, 256, 3, 1, 1, 0),
+    (2, 96, 35, 288, 1, 1, 0, 0),      # Swin qkv, Cin not a multiple of 64 (TMA zero-fills the K tail)
+    (2, 96, 35, 384, 1, 1, 2, 0),      # Swin fc1 + exact GELU
+    (2, 384, 35, 96, 1, 1, 0, 1),      # Swin fc2 + residual
+    (1, 768, 18, 2304, 1, 1, 0, 0),    # Swin stage-3 qkv
 ]
 
 
@@ -61,8 +65,10 @@ def reference(cuda, x, w, b, r, k, stride, relu, rnd):
                  torch.from_numpy(b).to(cuda).double(), stride=stride, padding=k // 2)
     if r is not None:
         y = y + q(torch.from_numpy(r).to(cuda)).double()
-    if relu:
+    if relu == 1:
         y = F.relu(y)
+    elif relu == 2:
+        y = F.gelu(y)
     return y.float()
 
 

@@ -63,6 +63,12 @@ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
 __device__ __forceinline__ float ordered_to_float(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
+// epilogue activation: 0 none, 1 ReLU, 2 exact GELU (torch.nn.GELU default: 0.5 x (1 + erf(x / sqrt 2)))
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  return v;
+}
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 #endif

@@ -193,7 +193,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
     }
     if (p.relu) {
 #pragma unroll
-      for (int i = 0; i < NCOL; ++i) v[i] = fmaxf(v[i], 0.f);
+      for (int i = 0; i < NCOL; ++i) v[i] = apply_act(v[i], p.relu);
     }
 #pragma unroll
     for (int i = 0; i < NCOL; i += 8) {
@@ -205,7 +205,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
   } else if (!halo) {
     if (p.relu) {
 #pragma unroll
-      for (int i = 0; i < NCOL; ++i) v[i] = fmaxf(v[i], 0.f);
+      for (int i = 0; i < NCOL; ++i) v[i] = apply_act(v[i], p.relu);
     }
     const long long r = ((long long)img * p.g.H + (y - 1)) * p.g.W + (x - 1);
     float* o = (float*)p.out + r * p.Cout_pad + col;
@@ -412,9 +412,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               }
             }
           }
-          if (p.relu) {
+          if (p.relu == 1) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = F16 ? fminf(fmaxf(v[i], 0.f), 65504.f) : fmaxf(v[i], 0.f);
+          } else if (p.relu == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float gl = apply_act(v[i], 2); v[i] = F16 ? fminf(fmaxf(gl, -65504.f), 65504.f) : gl; }
           } else if (F16) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -65504.f), 65504.f);
@@ -503,6 +506,8 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 
 static int pick_bn(int cout_pad) {
   if (cout_pad % 256 == 0) return 256;
+  for (int bn = 224; bn >= 64; bn -= 32)                               // largest 32-multiple divisor: 1152 -> 192, 288 -> 96
+    if (cout_pad % bn == 0 && cout_pad > 256) return bn;
   if (cout_pad <= 256 && cout_pad % 16 == 0) return cout_pad;          // 32, 64, 128, ...
   if (cout_pad % 2 == 0 && (cout_pad / 2) % 16 == 0 && cout_pad / 2 <= 256) return cout_pad / 2;   // 352 -> 176
   return 0;
@@ -510,7 +515,7 @@ static int pick_bn(int cout_pad) {
 
 bool tc_supported(const ConvArgs& a) {
   if (a.act_dt != DT_BF16 && a.act_dt != DT_F16) return false;
-  if (a.Cin % TC_BK != 0) return false;
+  if (a.Cin % 8 != 0 || a.Cin_pad % TC_BK != 0 || a.Cin_pad < a.Cin) return false;
   if (a.out_mode == 0 && a.Cout != a.Cout_pad) return false;
   return pick_bn(a.Cout_pad) != 0;
 }
@@ -524,7 +529,7 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   pl->tmem_cols = cols;
   pl->tma_epi = (a.out_mode == 0 && pl->BN % 32 == 0) ? 1 : 0;
   const size_t b_stage = (size_t)pl->BN * TC_BK * 2;
-  const int num_kb = a.ntaps * a.Cin / TC_BK;
+  const int num_kb = a.ntaps * a.Cin_pad / TC_BK;
   const size_t budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers*/;
   pl->nres = (pl->tma_epi && a.residual) ? 2 : 0;                  // residual buffers per epilogue group
   if (pl->nres) if (const char* e = getenv("YOLACT_B200_NRES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) pl->nres = v; }
@@ -545,7 +550,7 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
     pl->stages = stages > 8 ? 8 : stages;
     pl->smem_bytes = (size_t)pl->stages * per_stage + epi_bytes + 1024 + 1024;
   }
-  const int Ktot = a.ntaps * a.Cin;
+  const int Ktot = a.ntaps * a.Cin_pad;
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
   int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, TC_BM, f16);
@@ -575,7 +580,7 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   p.M = (long long)a.B * a.g.plane();
   p.m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
   p.n_tiles = a.Cout_pad / pl->BN;
-  p.kb_per_tap = a.Cin / TC_BK;
+  p.kb_per_tap = a.Cin_pad / TC_BK;
   p.ntaps = a.ntaps;
   for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a, long long M) {
   const int lr = tid >> 2, lk = (tid & 3) * 4;         // loader: row lr, k offset lk..lk+3
   const T* in = (const T*)a.in;
   const T* w = (const T*)a.weight;
-  const int Ktot = a.ntaps * a.Cin;
+  const int Ktot = a.ntaps * a.Cin_pad;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a, long long M) {
     const long long arow = m0 + lr + a.tap_shift[t];
     const bool a_ok = (m0 + lr < M) && arow >= 0 && arow < a.in_rows;
     const T* ap = in + arow * a.Cin + lk;
-    const T* bp = w + (long long)(n0 + lr) * Ktot + (long long)t * a.Cin + lk;
-    for (int k0 = 0; k0 < a.Cin; k0 += SBK) {
+    const T* bp = w + (long long)(n0 + lr) * Ktot + (long long)t * a.Cin_pad + lk;
+    for (int k0 = 0; k0 < a.Cin_pad; k0 += SBK) {
       float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4];
-      if (a_ok) {
+      if (a_ok && k0 + lk < a.Cin) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) av[q] = Act<T>::ld(ap + k0 + q);
       }
@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a, long long M) {
       if (a.out_mode == 0) {
         if (c >= a.Cout) continue;
         if (res) v += Act<T>::ld(res + m * a.Cout + c);
-        if (a.relu) v = fmaxf(v, 0.f);
+        v = apply_act(v, a.relu);
         Act<T>::st((T*)a.out + m * a.Cout + c, halo ? 0.f : v);
       } else if (!halo) {
-        if (a.relu) v = fmaxf(v, 0.f);
+        v = apply_act(v, a.relu);
         const long long r = ((long long)n * a.g.H + (y - 1)) * a.g.W + (x - 1);
         ((float*)a.out)[r * a.Cout_pad + c] = v;
       }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a, long long M) {
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   const long long M = (long long)a.B * a.g.plane();
   dim3 grid((unsigned)((M + SBM - 1) / SBM), (unsigned)ceil_div(a.Cout_pad, SBN));
-  YB_REQUIRE(a.Cin % SBK == 0, YB_ERR_UNSUPPORTED, "conv_simt: Cin=%d not a multiple of %d", a.Cin, SBK);
+  YB_REQUIRE(a.Cin % 4 == 0 && a.Cin_pad % SBK == 0, YB_ERR_UNSUPPORTED, "conv_simt: Cin=%d / Cin_pad=%d", a.Cin, a.Cin_pad);
   YB_DISPATCH_DT(a.act_dt, (k_conv_simt<T><<<grid, 256, 0, s>>>(a, M)));
   YB_CHECK_LAUNCH();
   return YB_OK;

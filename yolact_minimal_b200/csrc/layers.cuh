@@ -37,9 +37,10 @@ struct ConvArgs {
   int B;                 // images in this call
   Geom g;                // geometry of the OUTPUT (== input geometry for stride 1 / parity planes)
   int Cin, Cout, Cout_pad;
+  int Cin_pad;           // per-tap K stride of the packed weights (Cin rounded up to 64; A columns beyond Cin read as 0)
   int ntaps;
   int tap_shift[kMaxTaps];   // row shift into `in` per tap (includes parity-plane offsets)
-  int relu;
+  int relu;              // activation: 0 none, 1 ReLU, 2 exact (erf) GELU
   int out_mode;          // 0: haloed NHWC act_dt, halo zeroed;  1: dense fp32 [B*H*W][Cout] (halo rows skipped)
   long long in_rows;     // total rows addressable in `in` (for bounds checks)
 };
@@ -74,6 +75,13 @@ int launch_head_finalize(const float* head /*[B*H*W][ld]*/, int ld, int B, int H
                          int coef_dim, int anchor_offset, int A_total, float* cls, float* box, float* coef,
                          cudaStream_t s);
 int launch_write_activation(const float* in_nchw, int dt, int B, int C, int H, void* out, cudaStream_t s);
+int launch_patch_embed(const float* img, const float* w /*[48][96]*/, const float* bias, const float* g, const float* be, void* out,
+                       int dt, int B, int S, int Hg, cudaStream_t s);
+int launch_layernorm(const void* in, void* out, const float* g, const float* be, int dt, int B, int C, int H, cudaStream_t s);
+int launch_patch_merge_ln(const void* in, void* out, const float* g, const float* be, int dt, int B, int C, int Hin, int Hout,
+                          cudaStream_t s);
+int launch_window_attention(const void* qkv, const float* qkv_bias, const float* table, void* out, int dt, int B, int H, int C, int nH,
+                            int shift, cudaStream_t s);
 int launch_read_activation(const void* in, int dt, int B, int C, int H, float* out_nchw, cudaStream_t s);
 
 }  // namespace yb

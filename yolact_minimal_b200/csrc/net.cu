@@ -34,13 +34,13 @@ struct ActBuf {
   bool dense_f32 = false;      // dense [B*H*W][C] fp32 scratch (head outputs)
 };
 
-enum OpKind { OP_STEM, OP_POOL, OP_SPLIT, OP_CONV, OP_UPADD, OP_UP2X, OP_HEADFIN };
+enum OpKind { OP_STEM, OP_POOL, OP_SPLIT, OP_CONV, OP_UPADD, OP_UP2X, OP_HEADFIN, OP_PATCH_EMBED, OP_LN, OP_ATTN, OP_MERGE_LN };
 enum ExtOut { EXT_NONE = 0, EXT_PROTO = 1 };
 
 struct ConvW {                 // one packed convolution
   std::string wname, bname, bnname;   // weight / bias / batch-norm prefix ("" if absent)
   std::vector<std::string> cat;        // head: concatenated convs (conf|box|coef)
-  int Cin = 0, Cout = 0, Cout_pad = 0, k = 1;
+  int Cin = 0, Cin_pad = 0, Cout = 0, Cout_pad = 0, k = 1;
   void* d_w = nullptr;         // packed [Cout_alloc][k*k*Cin] in act dtype
   float* d_b = nullptr;        // [Cout_alloc]
 };
@@ -52,6 +52,8 @@ struct Op {
   int stride = 1, relu = 0, out_mode = 0, ext = EXT_NONE;
   int level = 0;               // head level
   int aux = -1;                // extra scratch activation (stem: im2col rows)
+  std::string p0, p1, p2;      // Swin ops: parameter names (LayerNorm weight/bias; attention: qkv bias, rel-pos table)
+  int heads = 0, shift = 0;    // attention
   TcPlan* tc = nullptr;
 };
 
@@ -76,6 +78,8 @@ struct yb_net {
   float* d_anchors = nullptr;
   float* d_stem_w = nullptr;                // [7][7][3][64]
   float* d_stem_b = nullptr;
+  std::map<std::string, float*> d_vec;      // Swin: LayerNorm / attention parameters on the device (fp32)
+  float* d_pe_w = nullptr;                  // Swin patch embedding weights [48][96]
   void* d_stem_w16 = nullptr;               // 16-bit modes: [64][192] GEMM weights (k = (r*7+s)*3+ci)
   float* d_stem_b16 = nullptr;
   ConvArgs stem_args{};
@@ -107,7 +111,7 @@ int new_act(yb_net* net, int C, int H, int planes = 1, bool dense_f32 = false) {
 }
 
 int new_conv(yb_net* net, const std::string& wname, const std::string& bname, const std::string& bnname, int Cin, int Cout, int k) {
-  ConvW c; c.wname = wname; c.bname = bname; c.bnname = bnname; c.Cin = Cin; c.Cout = Cout; c.Cout_pad = Cout; c.k = k;
+  ConvW c; c.wname = wname; c.bname = bname; c.bnname = bnname; c.Cin = Cin; c.Cin_pad = (Cin + 63) / 64 * 64; c.Cout = Cout; c.Cout_pad = Cout; c.k = k;
   net->add_param(wname, (int64_t)Cout * Cin * k * k);
   if (!bname.empty()) net->add_param(bname, Cout);
   if (!bnname.empty()) {
@@ -143,6 +147,58 @@ void build_program(yb_net* net) {
   const int S = cfg.img_size;
   net->H1 = (S - 1) / 2 + 1;
   net->H2 = (net->H1 - 1) / 2 + 1;
+  int couts[4] = {-1, -1, -1, -1};
+  int fin[3] = {512, 1024, 2048};
+  if (cfg.depth == 0) {
+    // ---------------- Swin-T backbone (modules/swin_transformer.py:436-518) ----------------
+    const int depths[4] = {2, 2, 6, 2}, heads[4] = {3, 6, 12, 24};
+    fin[0] = 192; fin[1] = 384; fin[2] = 768;
+    int Hg = (S + 3) / 4;
+    net->H1 = Hg;
+    net->add_param("backbone.patch_embed.proj.weight", 96 * 3 * 4 * 4);
+    net->add_param("backbone.patch_embed.proj.bias", 96);
+    net->add_param("backbone.patch_embed.norm.weight", 96);
+    net->add_param("backbone.patch_embed.norm.bias", 96);
+    int x = new_act(net, 96, Hg);
+    { Op o; o.kind = OP_PATCH_EMBED; o.out = x; net->ops.push_back(o); }
+    auto add_ln = [&](int in, const std::string& name, int C) {
+      net->add_param(name + ".weight", C); net->add_param(name + ".bias", C);
+      const int out = new_act(net, C, net->acts[in].H);
+      Op o; o.kind = OP_LN; o.in = in; o.out = out; o.p0 = name + ".weight"; o.p1 = name + ".bias";
+      net->ops.push_back(o);
+      return out;
+    };
+    for (int s = 0; s < 4; ++s) {
+      const int C = 96 << s;
+      for (int b = 0; b < depths[s]; ++b) {
+        const std::string p = "backbone.layers." + std::to_string(s) + ".blocks." + std::to_string(b);
+        const int t1 = add_ln(x, p + ".norm1", C);
+        net->add_param(p + ".attn.relative_position_bias_table", 169 * heads[s]);
+        const int cq = new_conv(net, p + ".attn.qkv.weight", p + ".attn.qkv.bias", "", C, 3 * C, 1);
+        const int cp = new_conv(net, p + ".attn.proj.weight", p + ".attn.proj.bias", "", C, C, 1);
+        const int qkv = add_conv(net, t1, cq, 1, 0);
+        const int att = new_act(net, C, net->acts[x].H);
+        { Op o; o.kind = OP_ATTN; o.in = qkv; o.out = att; o.p0 = p + ".attn.qkv.bias"; o.p1 = p + ".attn.relative_position_bias_table";
+          o.heads = heads[s]; o.shift = (b % 2) ? 3 : 0; net->ops.push_back(o); }
+        x = add_conv(net, att, cp, 1, 0, x);                         // x + proj(attn)
+        const int t2 = add_ln(x, p + ".norm2", C);
+        const int c1 = new_conv(net, p + ".mlp.fc1.weight", p + ".mlp.fc1.bias", "", C, 4 * C, 1);
+        const int c2 = new_conv(net, p + ".mlp.fc2.weight", p + ".mlp.fc2.bias", "", 4 * C, C, 1);
+        const int h = add_conv(net, t2, c1, 1, 2);                   // GELU
+        x = add_conv(net, h, c2, 1, 0, x);                           // x + fc2(gelu(fc1(norm2 x)))
+      }
+      if (s > 0) couts[s] = add_ln(x, "backbone.norm" + std::to_string(s), C);
+      if (s < 3) {
+        const std::string p = "backbone.layers." + std::to_string(s) + ".downsample";
+        const int Hin = net->acts[x].H, Hout = (Hin + 1) / 2;
+        net->add_param(p + ".norm.weight", 4 * C); net->add_param(p + ".norm.bias", 4 * C);
+        const int mg = new_act(net, 4 * C, Hout);
+        { Op o; o.kind = OP_MERGE_LN; o.in = x; o.out = mg; o.p0 = p + ".norm.weight"; o.p1 = p + ".norm.bias"; net->ops.push_back(o); }
+        x = add_conv(net, mg, new_conv(net, p + ".reduction.weight", "", "", 4 * C, 2 * C, 1), 1, 0);
+      }
+    }
+    net->taps["c3"] = couts[1]; net->taps["c4"] = couts[2]; net->taps["c5"] = couts[3];
+  } else {
   // stem (direct kernel; parameters registered by hand)
   net->add_param("backbone.conv1.weight", 64 * 3 * 7 * 7);
   for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) net->add_param(std::string("backbone.bn1") + s, 64);
@@ -155,7 +211,6 @@ void build_program(yb_net* net) {
   const int nblk50[4] = {3, 4, 6, 3}, nblk101[4] = {3, 4, 23, 3};
   const int* nblk = cfg.depth == 50 ? nblk50 : nblk101;
   int inpl = 64;
-  int couts[4];
   for (int s = 0; s < 4; ++s) {
     const int planes = 64 << s;
     for (int b = 0; b < nblk[s]; ++b) {
@@ -176,9 +231,9 @@ void build_program(yb_net* net) {
     couts[s] = x;
   }
   net->taps["c2"] = couts[0]; net->taps["c3"] = couts[1]; net->taps["c4"] = couts[2]; net->taps["c5"] = couts[3];
+  }
 
   // FPN (modules/yolact.py:73-89)
-  const int fin[3] = {512, 1024, 2048};
   int lat[3], pred[3];
   for (int i = 0; i < 3; ++i) {
     const std::string n = "fpn.lat_layers." + std::to_string(i);
@@ -222,7 +277,7 @@ void build_program(yb_net* net) {
   // prediction heads, shared weights over 5 levels (modules/yolact.py:12-31,:149-157)
   const int R = cfg.num_ratios, NC = cfg.num_classes, K = cfg.coef_dim;
   const int upf = new_conv(net, "prediction_layers.upfeature.0.weight", "prediction_layers.upfeature.0.bias", "", 256, 256, 3);
-  ConvW hc; hc.Cin = 256; hc.k = 3; hc.Cout = R * (NC + 4 + K); hc.Cout_pad = (hc.Cout + 15) / 16 * 16;
+  ConvW hc; hc.Cin = 256; hc.Cin_pad = 256; hc.k = 3; hc.Cout = R * (NC + 4 + K); hc.Cout_pad = (hc.Cout + 15) / 16 * 16;
   hc.cat = {"prediction_layers.conf_layer", "prediction_layers.bbox_layer", "prediction_layers.coef_layer.0"};
   net->add_param("prediction_layers.bbox_layer.weight", (int64_t)R * 4 * 256 * 9);
   net->add_param("prediction_layers.bbox_layer.bias", R * 4);
@@ -321,7 +376,7 @@ void bn_fold(const yb_net* net, const std::string& bn, int C, std::vector<float>
 }
 
 int pack_conv(yb_net* net, ConvW& c) {
-  const int k2 = c.k * c.k, Ktot = k2 * c.Cin;
+  const int k2 = c.k * c.k, Ktot = k2 * c.Cin_pad;
   const int Cout_alloc = (c.Cout_pad + 63) / 64 * 64;
   std::vector<float> w((size_t)Cout_alloc * Ktot, 0.f), bias(Cout_alloc, 0.f);
   auto pack_one = [&](const std::vector<float>& src, int cout, int row0, const std::vector<float>* scale) {
@@ -329,7 +384,7 @@ int pack_conv(yb_net* net, ConvW& c) {
     for (int co = 0; co < cout; ++co)
       for (int ci = 0; ci < c.Cin; ++ci)
         for (int t = 0; t < k2; ++t)
-          w[(size_t)(row0 + co) * Ktot + (size_t)t * c.Cin + ci] = src[((size_t)co * c.Cin + ci) * k2 + t] * (scale ? (*scale)[co] : 1.f);
+          w[(size_t)(row0 + co) * Ktot + (size_t)t * c.Cin_pad + ci] = src[((size_t)co * c.Cin + ci) * k2 + t] * (scale ? (*scale)[co] : 1.f);
   };
   if (c.cat.empty()) {
     std::vector<float> s, t;
@@ -377,7 +432,7 @@ void conv_args(const yb_net* net, const Op& o, int B, ConvArgs* a, void* ext_out
   a->out = o.ext != EXT_NONE ? ext_out : act_ptr(net, o.out);
   a->act_dt = net->act_dt; a->B = B;
   a->g.H = in.H; a->g.W = in.H;
-  a->Cin = c.Cin; a->Cout = c.Cout; a->Cout_pad = c.Cout_pad;
+  a->Cin = c.Cin; a->Cin_pad = c.Cin_pad; a->Cout = c.Cout; a->Cout_pad = c.Cout_pad;
   a->relu = o.relu; a->out_mode = o.out_mode;
   const int Wp = in.H + 2;
   const long long plane_rows = (long long)net->max_batch * Wp * Wp;      // parity planes sit at max-batch strides
@@ -406,7 +461,7 @@ void conv_args(const yb_net* net, const Op& o, int B, ConvArgs* a, void* ext_out
 // ================================================================================================
 extern "C" int yb_net_create(const yb_net_config* cfg, yb_net** out) {
   YB_REQUIRE(cfg && out, YB_ERR_INVALID, "yb_net_create: NULL argument");
-  YB_REQUIRE(cfg->depth == 50 || cfg->depth == 101, YB_ERR_UNSUPPORTED, "yb_net_create: depth=%d (50 or 101)", cfg->depth);
+  YB_REQUIRE(cfg->depth == 50 || cfg->depth == 101 || cfg->depth == 0, YB_ERR_UNSUPPORTED, "yb_net_create: depth=%d (50, 101, or 0 = Swin-T)", cfg->depth);
   YB_REQUIRE(cfg->img_size >= 64 && cfg->img_size <= 4096, YB_ERR_INVALID, "yb_net_create: img_size=%d", cfg->img_size);
   YB_REQUIRE(cfg->num_classes >= 2 && cfg->num_ratios >= 1 && cfg->num_ratios <= 3, YB_ERR_INVALID, "yb_net_create: num_classes=%d num_ratios=%d", cfg->num_classes, cfg->num_ratios);
   YB_REQUIRE(cfg->coef_dim > 0 && cfg->coef_dim % 4 == 0 && cfg->coef_dim <= 64, YB_ERR_UNSUPPORTED, "yb_net_create: coef_dim=%d", cfg->coef_dim);
@@ -422,6 +477,8 @@ extern "C" void yb_net_destroy(yb_net* net) {
   for (void* p : net->slots) cudaFree(p);
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); }
   for (auto& o : net->ops) tc_plan_destroy(o.tc);
+  for (auto& kv : net->d_vec) cudaFree(kv.second);
+  cudaFree(net->d_pe_w);
   for (void* p : {(void*)net->d_anchors, (void*)net->d_stem_w, (void*)net->d_stem_b, net->d_stem_w16, (void*)net->d_stem_b16, (void*)net->d_img, (void*)net->d_cls,
                   (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws, (void*)net->d_cnt, (void*)net->d_ocls,
                   (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
@@ -477,7 +534,22 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
     YB_CHECK_CUDA(cudaMemset(net->slots[s], 0, net->slot_bytes[s]));
   }
   for (auto& c : net->convs) YB_PROPAGATE(pack_conv(net, c));
-  {  // stem: [64][3][7][7] * bn scale -> [7][7][3][64]
+  for (auto& kv : net->d_vec) cudaFree(kv.second);
+  net->d_vec.clear();
+  cudaFree(net->d_pe_w); net->d_pe_w = nullptr;
+  if (net->cfg.depth == 0) {
+    // Swin: LayerNorm / attention vectors as they are; patch-embed weights [96][3][4][4] -> [48][96]
+    for (const Op& o : net->ops)
+      for (const std::string* nm : {&o.p0, &o.p1})
+        if (!nm->empty() && !net->d_vec.count(*nm)) { float* d = nullptr; const auto& v = net->P_(*nm); YB_PROPAGATE(upload(v.data(), v.size() * 4, (void**)&d)); net->d_vec[*nm] = d; }
+    for (const char* nm : {"backbone.patch_embed.proj.bias", "backbone.patch_embed.norm.weight", "backbone.patch_embed.norm.bias"}) {
+      float* d = nullptr; const auto& v = net->P_(nm); YB_PROPAGATE(upload(v.data(), v.size() * 4, (void**)&d)); net->d_vec[nm] = d;
+    }
+    const auto& src = net->P_("backbone.patch_embed.proj.weight");
+    std::vector<float> w(48 * 96);
+    for (int co = 0; co < 96; ++co) for (int k = 0; k < 48; ++k) w[k * 96 + co] = src[co * 48 + k];
+    YB_PROPAGATE(upload(w.data(), w.size() * 4, (void**)&net->d_pe_w));
+  } else {  // stem: [64][3][7][7] * bn scale -> [7][7][3][64]
     std::vector<float> s, t, w(147 * 64);
     bn_fold(net, "backbone.bn1", 64, s, t);
     const auto& src = net->P_("backbone.conv1.weight");
@@ -491,7 +563,7 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   YB_PROPAGATE(upload(net->anchors.data(), net->anchors.size() * 4, (void**)&net->d_anchors));
   // tensor-core plans (16-bit operand modes)
   if (net->act_dt != DT_F32 && !getenv("YOLACT_B200_NO_TC")) {
-    {  // stem as a GEMM over im2col rows: [B*(H1+2)^2][192] x [192][64]
+    if (net->cfg.depth != 0) {  // stem as a GEMM over im2col rows: [B*(H1+2)^2][192] x [192][64]
       std::vector<float> sc, sh, w((size_t)64 * 192, 0.f);
       bn_fold(net, "backbone.bn1", 64, sc, sh);
       const auto& src = net->P_("backbone.conv1.weight");
@@ -505,7 +577,7 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
       ConvArgs& a = net->stem_args;
       memset(&a, 0, sizeof(a));
       a.in = act_ptr(net, so.aux); a.weight = net->d_stem_w16; a.bias = net->d_stem_b16; a.out = act_ptr(net, so.out);
-      a.act_dt = net->act_dt; a.B = max_batch; a.g.H = net->H1; a.g.W = net->H1; a.Cin = 192; a.Cout = 64; a.Cout_pad = 64;
+      a.act_dt = net->act_dt; a.B = max_batch; a.g.H = net->H1; a.g.W = net->H1; a.Cin = 192; a.Cin_pad = 192; a.Cout = 64; a.Cout_pad = 64;
       a.ntaps = 1; a.tap_shift[0] = 0; a.relu = 1; a.out_mode = 0;
       a.in_rows = (long long)max_batch * (net->H1 + 2) * (net->H1 + 2);
       YB_PROPAGATE(tc_plan_create(a, max_batch, &so.tc));
@@ -584,6 +656,23 @@ extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* c
       case OP_UP2X:
         YB_PROPAGATE(launch_upsample2x_ac(act_ptr(net, o.in), act_ptr(net, o.out), net->act_dt, batch, 256, net->acts[o.in].H, s));
         break;
+      case OP_PATCH_EMBED:
+        YB_PROPAGATE(launch_patch_embed(img, net->d_pe_w, net->d_vec.at("backbone.patch_embed.proj.bias"),
+                                        net->d_vec.at("backbone.patch_embed.norm.weight"), net->d_vec.at("backbone.patch_embed.norm.bias"),
+                                        act_ptr(net, o.out), net->act_dt, batch, cfg.img_size, net->acts[o.out].H, s));
+        break;
+      case OP_LN:
+        YB_PROPAGATE(launch_layernorm(act_ptr(net, o.in), act_ptr(net, o.out), net->d_vec.at(o.p0), net->d_vec.at(o.p1), net->act_dt, batch,
+                                      net->acts[o.in].C, net->acts[o.in].H, s));
+        break;
+      case OP_ATTN:
+        YB_PROPAGATE(launch_window_attention(act_ptr(net, o.in), net->d_vec.at(o.p0), net->d_vec.at(o.p1), act_ptr(net, o.out), net->act_dt,
+                                             batch, net->acts[o.out].H, net->acts[o.out].C, o.heads, o.shift, s));
+        break;
+      case OP_MERGE_LN:
+        YB_PROPAGATE(launch_patch_merge_ln(act_ptr(net, o.in), act_ptr(net, o.out), net->d_vec.at(o.p0), net->d_vec.at(o.p1), net->act_dt,
+                                           batch, net->acts[o.in].C, net->acts[o.in].H, net->acts[o.out].H, s));
+        break;
       case OP_HEADFIN: {
         const ActBuf& h = net->acts[o.in];
         YB_PROPAGATE(launch_head_finalize((const float*)act_ptr(net, o.in), h.C, batch, h.H * h.H, cfg.num_ratios, cfg.num_classes,
@@ -604,8 +693,9 @@ extern "C" int yb_net_set_profiling(yb_net* net, int enable) {
 
 extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, int* num_entries) {
   YB_REQUIRE(net && out && num_entries, YB_ERR_INVALID, "yb_net_profile: NULL argument");
-  static const char* kNames[] = {"conv_tc", "conv_simt", "stem", "maxpool", "phase_split", "upsample_add", "upsample2x", "head_finalize"};
-  const int NK = 8;
+  static const char* kNames[] = {"conv_tc", "conv_simt", "stem", "maxpool", "phase_split", "upsample_add", "upsample2x", "head_finalize",
+                                 "patch_embed", "layernorm", "window_attention", "patch_merge_ln"};
+  const int NK = 12;
   YB_REQUIRE(max_entries >= NK, YB_ERR_INVALID, "yb_net_profile: need room for %d entries", NK);
   for (int i = 0; i < NK; ++i) { memset(&out[i], 0, sizeof(out[i])); strncpy(out[i].name, kNames[i], sizeof(out[i].name) - 1); }
   const size_t esz = dtype_size(net->act_dt);
@@ -637,6 +727,11 @@ extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, 
         case OP_UPADD: { k = 5; const ActBuf& a = net->acts[o.out]; bytes = 2.25 * B * a.H * a.H * a.C * esz; break; }
         case OP_UP2X: { k = 6; const ActBuf& a = net->acts[o.out]; bytes = 1.25 * B * a.H * a.H * a.C * esz; break; }
         case OP_HEADFIN: { k = 7; const ActBuf& a = net->acts[o.in]; bytes = 2.0 * B * a.H * a.H * a.C * 4; break; }
+        case OP_PATCH_EMBED: { k = 8; const ActBuf& a = net->acts[o.out]; flops = 2.0 * B * a.H * a.H * 96 * 48; bytes = B * 3.0 * net->cfg.img_size * net->cfg.img_size * 4 + B * a.H * a.H * 96.0 * esz; break; }
+        case OP_LN: { k = 9; const ActBuf& a = net->acts[o.out]; bytes = 2.0 * B * a.H * a.H * a.C * esz; break; }
+        case OP_ATTN: { k = 10; const ActBuf& a = net->acts[o.out]; const double nw = ((a.H + 6) / 7) * ((a.H + 6) / 7);
+                        flops = B * nw * o.heads * 4.0 * 49 * 49 * 32; bytes = 4.0 * B * a.H * a.H * a.C * esz; break; }
+        case OP_MERGE_LN: { k = 11; const ActBuf& a = net->acts[o.out]; bytes = 2.0 * B * a.H * a.H * a.C * esz; break; }
       }
       if (dump) {
         const ConvW* c = o.kind == OP_CONV ? &net->convs[o.conv] : nullptr;
@@ -735,14 +830,15 @@ extern "C" int yb_conv2d(const float* x, int batch, int cin, int h, const float*
                          int stride, int relu, const float* residual, int precision, int use_tc, float* out) {
   YB_REQUIRE(x && w && out, YB_ERR_INVALID, "yb_conv2d: NULL argument");
   YB_REQUIRE((k == 1 || k == 3) && (stride == 1 || stride == 2), YB_ERR_UNSUPPORTED, "yb_conv2d: k=%d stride=%d", k, stride);
-  YB_REQUIRE(cin % 64 == 0 && cout >= 1 && batch >= 1 && h >= 1, YB_ERR_UNSUPPORTED, "yb_conv2d: cin=%d cout=%d", cin, cout);
+  YB_REQUIRE(cin % 8 == 0 && cout >= 1 && batch >= 1 && h >= 1, YB_ERR_UNSUPPORTED, "yb_conv2d: cin=%d cout=%d", cin, cout);
+  const int cin_pad = (cin + 63) / 64 * 64;
   YB_REQUIRE(precision >= 0 && precision <= 2, YB_ERR_INVALID, "yb_conv2d: precision=%d", precision);
   const int dt = precision == YB_PREC_BF16 ? DT_BF16 : (precision == YB_PREC_FP16 ? DT_F16 : DT_F32);
   const size_t esz = dtype_size(dt);
   const int ho = stride == 2 ? (h - 1) / 2 + 1 : h;
   const int planes = stride == 2 ? (k == 3 ? 4 : 1) : 1;
   const int cout_pad = (cout + 15) / 16 * 16, cout_alloc = (cout_pad + 63) / 64 * 64;
-  const int k2 = k * k, Ktot = k2 * cin;
+  const int k2 = k * k, Ktot = k2 * cin_pad;
   Scratch sc;
   void *d_in = nullptr, *d_split = nullptr, *d_out = nullptr, *d_res = nullptr, *d_w = nullptr; float* d_b = nullptr;
   const size_t in_rows = (size_t)batch * (h + 2) * (h + 2), out_rows = (size_t)batch * (ho + 2) * (ho + 2);
@@ -760,7 +856,7 @@ extern "C" int yb_conv2d(const float* x, int batch, int cin, int h, const float*
   std::vector<float> wp((size_t)cout_alloc * Ktot, 0.f), bp(cout_alloc, 0.f);
   for (int co = 0; co < cout; ++co) {
     for (int ci = 0; ci < cin; ++ci)
-      for (int t = 0; t < k2; ++t) wp[(size_t)co * Ktot + (size_t)t * cin + ci] = w[((size_t)co * cin + ci) * k2 + t];
+      for (int t = 0; t < k2; ++t) wp[(size_t)co * Ktot + (size_t)t * cin_pad + ci] = w[((size_t)co * cin + ci) * k2 + t];
     bp[co] = bias ? bias[co] : 0.f;
   }
   YB_PROPAGATE(sc.alloc(&d_w, wp.size() * esz));
@@ -773,7 +869,7 @@ extern "C" int yb_conv2d(const float* x, int batch, int cin, int h, const float*
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.in = stride == 2 ? d_split : d_in; a.weight = d_w; a.bias = d_b; a.residual = d_res; a.out = d_out;
-  a.act_dt = dt; a.B = batch; a.g.H = ho; a.g.W = ho; a.Cin = cin; a.Cout = cout; a.Cout_pad = cout; a.relu = relu; a.out_mode = 0;
+  a.act_dt = dt; a.B = batch; a.g.H = ho; a.g.W = ho; a.Cin = cin; a.Cin_pad = cin_pad; a.Cout = cout; a.Cout_pad = cout; a.relu = relu; a.out_mode = 0;
   YB_REQUIRE(cout % 16 == 0 || !use_tc, YB_ERR_UNSUPPORTED, "yb_conv2d: tc path needs cout %% 16 == 0");
   const int Wp = ho + 2;
   if (stride == 1) {

@@ -5,8 +5,8 @@ attributes (.cfg, .coef_dim, .backbone, .fpn, .proto_net, .prediction_layers, .a
 proto_out [B,P,P,32])`.  The submodules are parameter containers; the forward pass is the
 CUDA layer program in libyolact_b200.so, driven through yolact_minimal_b200.engine.Engine.
 
-Not built yet (raises, never falls back): the training branch of forward (compute_loss,
-modules/yolact.py:159-161,:166-313) and the Swin-T backbone (`swin_tiny_*` configs).
+Backbones: ResNet-50/101 and Swin-T (`swin_tiny_*` configs).  Not built yet (raises, never falls
+back): the training branch of forward (compute_loss, modules/yolact.py:159-161,:166-313).
 """
 import math
 import os
@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from .resnet import ResNet, _no_forward
+from .swin_transformer import SwinTransformer
 from ..engine import Engine
 from ..utils.box_utils import all_anchors
 
@@ -69,11 +70,15 @@ class Yolact(nn.Module):
         elif name.startswith('res50'):
             self.depth, blocks = 50, (3, 4, 6, 3)
         elif name.startswith('swin_tiny'):
-            raise NotImplementedError('swin_tiny backbone is not built yet in yolact_minimal_b200 (SURVEY.md 8 row a2)')
+            self.depth, blocks = 0, None                      # depth 0 selects the Swin-T layer program in the engine
         else:
             raise ValueError(f'config class {name!r} does not select a backbone (res101*/res50*/swin_tiny*)')
-        self.backbone = ResNet(blocks)
-        self.fpn = FPN((512, 1024, 2048))
+        if blocks is None:
+            self.backbone = SwinTransformer()
+            self.fpn = FPN((192, 384, 768))
+        else:
+            self.backbone = ResNet(blocks)
+            self.fpn = FPN((512, 1024, 2048))
         self.proto_net = ProtoNet(self.coef_dim)
         self.prediction_layers = PredictionModule(cfg, self.coef_dim)
         self.anchors = all_anchors(cfg)                       # python list, like the reference (yolact.py:111-114)
