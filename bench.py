@@ -30,7 +30,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ARCH, IMG, BATCH = 'res101', 550, 64
-GFLOP_PER_IMG = 164.68          # algorithmic 2*MAC of the reference forward, res101 @ 550
+# algorithmic 2*MAC of the reference forward per image
+GFLOPS = {('res101', 550): 164.68, ('res101', 544): 157.16, ('res50', 550): 118.28, ('res50', 544): 113.38,
+          ('swin_tiny', 550): 123.43, ('swin_tiny', 544): 119.19}
+GFLOP_PER_IMG = GFLOPS[(ARCH, IMG)]
 
 
 def host_cores():
@@ -323,7 +326,12 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--precision', default=os.environ.get('YOLACT_B200_PRECISION', 'fp16'), choices=['fp16', 'bf16', 'fp32'])
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--arch', default=ARCH, choices=['res101', 'res50', 'swin_tiny'], help='default: the BASELINE metric config')
+    ap.add_argument('--img', type=int, default=IMG)
+    ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU')
     args = ap.parse_args()
+    ARCH, IMG, BATCH = args.arch, args.img, args.batch
+    GFLOP_PER_IMG = GFLOPS.get((ARCH, IMG), float('nan'))
     if args.impl == 'reference':
         run_reference(args)
     else:

