@@ -282,8 +282,13 @@ def run_ours(args):
     dom = 'k_conv_tc' if prof['conv_tc']['launches'] else 'k_conv_simt'
     achieved = tc['flops'] / (tc['ms'] * 1e-3) / 1e12 if tc['ms'] else 0.0
     total_ms = sum(v['ms'] for v in prof.values())
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tpath) and dom == 'k_conv_tc':
+        traffic = json.load(open(tpath)).get('dram_bytes_per_launch_avg')      # from the committed ncu --set full capture
     roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tf_sustained'], 'traffic': None, 'peak_source': pk['src'] + ' (sustained bf16 cuBLAS)',
+                'frac': achieved / pk['tf_sustained'], 'traffic': traffic,
+                'alg_bytes_per_launch': tc['bytes'] / max(1, tc['launches']), 'peak_source': pk['src'] + ' (sustained bf16 cuBLAS)',
                 'launches_per_step': tc['launches'] / max(1, tc['forwards']),
                 'share_of_forward': tc['ms'] / total_ms if total_ms else None,
                 'alg_flops_per_launch': tc['flops'] / max(1, tc['launches']),
