@@ -212,11 +212,12 @@ __global__ void __launch_bounds__(256) k_stem(const float* __restrict__ img, con
 // 16-bit modes: the stem runs on the tensor cores as a GEMM with K = 7*7*3 = 147 padded to 192.
 // This kernel writes the im2col rows in the haloed geometry of the stem OUTPUT:
 // cols[(b, yp, xp)][k], k = (r*7+s)*3 + ci  <- img[b, ci, 2(yp-1)+r-3, 2(xp-1)+s-3]  (0 outside / halo / k >= 147)
+constexpr int kStemK = 152;                      // 7*7*3 = 147 rounded up to a multiple of 8 (16-byte TMA rows)
 constexpr int IC_PX = 64;                       // output pixels per block (one haloed row segment)
 constexpr int IC_W = 2 * IC_PX + 6;             // staged input columns (134)
 template <typename T>
 __global__ void __launch_bounds__(256) k_stem_im2col(const float* __restrict__ img, T* __restrict__ cols, int B, int S, int H1) {
-  constexpr int KP = 192, N = 8, KV = KP / N;
+  constexpr int KP = kStemK, N = 8, KV = KP / N;
   __shared__ float s_in[3][7][IC_W + 2];
   const int Hp = H1 + 2;
   const int b = blockIdx.z, yp = blockIdx.y, xp0 = blockIdx.x * IC_PX, tid = threadIdx.x;

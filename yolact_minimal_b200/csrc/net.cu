@@ -90,6 +90,10 @@ struct yb_net {
   int host_batch = 0; int host_maxdet = 0;
   cudaStream_t own_stream = nullptr;
   bool profiling = false;
+  // CUDA graphs of (forward + post-process) for the host-buffer entry point, keyed by batch + params
+  struct HostGraph { cudaGraphExec_t exec; uint64_t launches; };
+  std::map<std::string, HostGraph> host_graphs;
+  void drop_graphs() { for (auto& kv : host_graphs) cudaGraphExecDestroy(kv.second.exec); host_graphs.clear(); }
   std::vector<std::vector<cudaEvent_t>> prof_sets;   // one event list per profiled forward
   std::vector<int> prof_batch;
 
@@ -203,7 +207,7 @@ void build_program(yb_net* net) {
   net->add_param("backbone.conv1.weight", 64 * 3 * 7 * 7);
   for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) net->add_param(std::string("backbone.bn1") + s, 64);
   const int stem = new_act(net, 64, net->H1);
-  const int stem_cols = new_act(net, 192, net->H1);
+  const int stem_cols = new_act(net, 152, net->H1);          // im2col rows: K = 147 padded to 152 (kernels_simt.cu kStemK)
   { Op o; o.kind = OP_STEM; o.out = stem; o.aux = stem_cols; net->ops.push_back(o); }
   int x = new_act(net, 64, net->H2);
   { Op o; o.kind = OP_POOL; o.in = stem; o.out = x; net->ops.push_back(o); }
@@ -483,6 +487,7 @@ extern "C" void yb_net_destroy(yb_net* net) {
                   (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws, (void*)net->d_cnt, (void*)net->d_ocls,
                   (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
     cudaFree(p);
+  net->drop_graphs();
   if (net->own_stream) cudaStreamDestroy(net->own_stream);
   delete net;
 }
@@ -518,6 +523,7 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   YB_PROPAGATE(yb_device_info(nullptr, &cc_major, nullptr));
   YB_REQUIRE(cc_major == 10, YB_ERR_UNSUPPORTED, "yb_net_finalize: this library is built for sm_100a only (device cc major %d)", cc_major);
   // release a previous finalisation
+  net->drop_graphs();
   for (void* p : net->slots) cudaFree(p);
   net->slots.clear();
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); c.d_w = nullptr; c.d_b = nullptr; }
@@ -577,7 +583,7 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
       ConvArgs& a = net->stem_args;
       memset(&a, 0, sizeof(a));
       a.in = act_ptr(net, so.aux); a.weight = net->d_stem_w16; a.bias = net->d_stem_b16; a.out = act_ptr(net, so.out);
-      a.act_dt = net->act_dt; a.B = max_batch; a.g.H = net->H1; a.g.W = net->H1; a.Cin = 192; a.Cin_pad = 192; a.Cout = 64; a.Cout_pad = 64;
+      a.act_dt = net->act_dt; a.B = max_batch; a.g.H = net->H1; a.g.W = net->H1; a.Cin = 152; a.Cin_pad = 192; a.Cout = 64; a.Cout_pad = 64;
       a.ntaps = 1; a.tap_shift[0] = 0; a.relu = 1; a.out_mode = 0;
       a.in_rows = (long long)max_batch * (net->H1 + 2) * (net->H1 + 2);
       YB_PROPAGATE(tc_plan_create(a, max_batch, &so.tc));
@@ -781,6 +787,7 @@ extern "C" int yb_net_detect_host(yb_net* net, const float* img_host, int batch,
   const size_t D = p->max_det;
   if (!net->own_stream) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&net->own_stream, cudaStreamNonBlocking));
   if (net->host_batch != (int)B || net->host_maxdet < (int)D) {
+    net->drop_graphs();
     for (void* q : {(void*)net->d_img, (void*)net->d_cls, (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws,
                     (void*)net->d_cnt, (void*)net->d_ocls, (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
       cudaFree(q);
@@ -804,9 +811,38 @@ extern "C" int yb_net_detect_host(yb_net* net, const float* img_host, int batch,
   cudaStream_t s = net->own_stream;
   const size_t b = batch;
   YB_CHECK_CUDA(cudaMemcpyAsync(net->d_img, img_host, b * 3 * S * S * 4, cudaMemcpyHostToDevice, s));
-  YB_PROPAGATE(yb_net_forward(net, net->d_img, batch, net->d_cls, net->d_box, net->d_coef, net->d_proto, s));
-  YB_PROPAGATE(yb_detect(net->d_cls, net->d_box, net->d_coef, net->d_anchors, batch, (int)A, p, net->d_ws, net->ws_bytes, net->d_cnt,
-                         net->d_ocls, net->d_oanc, net->d_osc, net->d_obox, out_coef ? net->d_ocoef : nullptr, s));
+  auto run = [&]() -> int {
+    YB_PROPAGATE(yb_net_forward(net, net->d_img, batch, net->d_cls, net->d_box, net->d_coef, net->d_proto, s));
+    YB_PROPAGATE(yb_detect(net->d_cls, net->d_box, net->d_coef, net->d_anchors, batch, (int)A, p, net->d_ws, net->ws_bytes, net->d_cnt,
+                           net->d_ocls, net->d_oanc, net->d_osc, net->d_obox, out_coef ? net->d_ocoef : nullptr, s));
+    return YB_OK;
+  };
+  if (net->profiling || getenv("YOLACT_B200_NO_GRAPH")) {
+    YB_PROPAGATE(run());
+  } else {
+    // ~150 kernel launches per call: capture once per (batch, params), replay afterwards
+    std::string key((const char*)p, sizeof(*p));
+    key += std::to_string(batch) + (out_coef ? "c" : "n");
+    auto it = net->host_graphs.find(key);
+    if (it == net->host_graphs.end()) {
+      YB_PROPAGATE(run());                                         // warm run: lazy one-time setup stays outside the capture
+      YB_CHECK_CUDA(cudaStreamSynchronize(s));
+      const uint64_t l0 = g_launches.load();
+      YB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int st = run();
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (st != YB_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+      YB_CHECK_CUDA(ce);
+      yb_net::HostGraph hg{nullptr, g_launches.load() - l0};
+      ce = cudaGraphInstantiate(&hg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      YB_CHECK_CUDA(ce);
+      it = net->host_graphs.emplace(key, hg).first;
+    }
+    YB_CHECK_CUDA(cudaGraphLaunch(it->second.exec, s));
+    count_launch(it->second.launches);
+  }
   YB_CHECK_CUDA(cudaMemcpyAsync(out_count, net->d_cnt, b * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_class, net->d_ocls, b * D * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_anchor, net->d_oanc, b * D * 4, cudaMemcpyDeviceToHost, s));

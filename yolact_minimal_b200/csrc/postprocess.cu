@@ -320,17 +320,24 @@ k_class_fast_nms(int A, int C1, int top_k, float iou_thr, DetectWs ws) {
     int j = (int)(((long long)256 * 4 * k + n - 1) / n) + 4;        // expected survivors ~ 4k + 4n/256
     if (j > 255) j = 255;
     const uint32_t cut = s_sample[j];
-    const int n_round = (n + 31) & ~31;
-    for (int i = tid; i < n_round; i += kThreads) {
-      const uint32_t key = i < n ? float_to_ordered(row[i]) : 0u;
-      const bool take = i < n && key >= cut;
-      const unsigned bal = __ballot_sync(kFull, take);
-      int base = 0;
-      if (lane == 0 && bal) base = atomicAdd(&s_m, __popc(bal));
-      base = __shfl_sync(kFull, base, 0);
-      if (take) {
-        const int pos = base + __popc(bal & ((1u << lane) - 1u));
-        if (pos < kCompactCap) { s_ckey[pos] = key; s_cidx[pos] = i; }
+    // 4 independent loads in flight per thread, then 4 ballot/append rounds
+    for (int i0 = 0; i0 < n; i0 += 4 * kThreads) {
+      uint32_t key[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * kThreads + tid; key[u] = i < n ? float_to_ordered(__ldg(row + i)) : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreads + tid;
+        const bool take = i < n && key[u] >= cut;
+        const unsigned bal = __ballot_sync(kFull, take);
+        if (bal == 0u) continue;                                   // warp-uniform
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
+        base = __shfl_sync(kFull, base, 0);
+        if (take) {
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (pos < kCompactCap) { s_ckey[pos] = key[u]; s_cidx[pos] = i; }
+        }
       }
     }
     __syncthreads();
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(kThreads)
 k_final_topk(const float* __restrict__ coef, int A, int C1, int max_det, int coef_dim, int traditional, float img_size,
              DetectWs ws, int32_t* out_count, int32_t* out_class, int32_t* out_anchor, float* out_score,
              float* out_box, float* out_coef) {
-  extern __shared__ int s_ccnt[];                  // [C1] min(cls_cnt, max_det)
+  extern __shared__ int s_ccnt[];                  // [C1] min(cls_cnt, max_det), then [C1*max_det] keys, [C1*max_det] tie keys
   __shared__ unsigned long long s_sort[kSortCap];
   __shared__ int s_idx[kSortCap];
   __shared__ int s_hist[256];
@@ -511,12 +518,22 @@ k_final_topk(const float* __restrict__ coef, int A, int C1, int max_det, int coe
   const int dense = C1 * max_det;
   const float* cscore = ws.cls_score + (size_t)b * C1 * KC;
   const int* canchor = ws.cls_anchor + (size_t)b * C1 * KC;
-  auto valid_key = [&](int i, uint32_t& key, uint32_t& sec) -> bool {
+  // stage the (score key, tie key) of every surviving candidate in shared memory once; key 0 = empty slot
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_ccnt + ((C1 + 3) & ~3));
+  uint32_t* s_sec = s_key + dense;
+  for (int i = tid; i < dense; i += kThreads) {
     const int c = i / max_det, r = i - c * max_det;
-    if (r >= s_ccnt[c]) return false;
-    key = float_to_ordered(cscore[c * KC + r]);
-    sec = (uint32_t)c * (uint32_t)A + (uint32_t)canchor[c * KC + r];   // class-major, anchor-ascending tie order
-    return true;
+    uint32_t key = 0, sec = 0xFFFFFFFFu;
+    if (r < s_ccnt[c]) {
+      key = float_to_ordered(cscore[c * KC + r]);
+      sec = (uint32_t)c * (uint32_t)A + (uint32_t)canchor[c * KC + r];   // class-major, anchor-ascending tie order
+    }
+    s_key[i] = key; s_sec[i] = sec;
+  }
+  __syncthreads();
+  auto valid_key = [&](int i, uint32_t& key, uint32_t& sec) -> bool {
+    key = s_key[i]; sec = s_sec[i];
+    return key != 0u;
   };
   if (total > d) {
     SelectResult r = block_select_kth_largest(dense, d, [&](int i, uint32_t& v) { uint32_t s; return valid_key(i, v, s); }, s_hist, s_tmp);
@@ -695,7 +712,9 @@ extern "C" int yb_detect(const float* cls, const float* box, const float* coef, 
     YB_CHECK_LAUNCH();
   }
   {
-    const size_t smem = (size_t)C1 * sizeof(int);
+    const size_t smem = (size_t)((C1 + 3) & ~3) * sizeof(int) + (size_t)2 * C1 * p->max_det * sizeof(uint32_t);
+    YB_REQUIRE(smem <= 200 * 1024, YB_ERR_UNSUPPORTED, "yb_detect: (C-1)*max_det = %d too large for the final top-k stage", C1 * p->max_det);
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_final_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_final_topk<<<B, kThreads, smem, stream>>>(coef, A, C1, p->max_det, p->coef_dim, p->traditional, p->img_size, ws,
                                                  out_count, out_class, out_anchor, out_score, out_box, out_coef);
     YB_CHECK_LAUNCH();
