@@ -270,7 +270,7 @@ __device__ void bitonic_sort_256_desc_u32(uint32_t* key) {
 
 // IoU(a,b) <= thr with the reference's fp32 rounding (utils/box_utils.py:28-36): a 2-instruction
 // reciprocal estimate decides unless it lands within 4e-6 of the threshold, where the exactly
-// rounded division is used (also covers NaN: 0/0 falls through to the exact path and compares false).
+// rounded division is used.
 __device__ __forceinline__ bool iou_le(float4 a, float area_a, float4 b, float area_b, float thr) {
   float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
   float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
@@ -278,7 +278,8 @@ __device__ __forceinline__ bool iou_le(float4 a, float area_a, float4 b, float a
   h = h < 0.f ? 0.f : h;
   const float inter = __fmul_rn(w, h);
   const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-  const float q = inter * __frcp_rn(uni);
+  const float q = __fdividef(inter, uni);            // MUFU.RCP + FMUL, <= 2 ulp
+  if (q != q) return false;                          // 0/0 (two zero-area boxes): NaN <= thr is false, exactly as the IEEE quotient
   if (fabsf(q - thr) > 4e-6f) return q <= thr;
   return __fdiv_rn(inter, uni) <= thr;
 }
