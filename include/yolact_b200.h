@@ -189,6 +189,15 @@ YB_API int yb_net_detect_host(yb_net* net, const float* img_host, int batch, con
                        float* out_score, float* out_box, float* out_coef);
 YB_API const float* yb_net_last_proto(const yb_net* net);
 
+/* Pipelined form of yb_net_detect_host for streams of batches: submit() enqueues
+ * H2D(img) -> forward -> post-process -> D2H(records) on the net's own streams and returns at once;
+ * collect() blocks until that submission's records are in the caller's buffers.  Up to two
+ * submissions may be in flight, so the host->device copy of batch i+1 overlaps the compute of batch i.
+ * img_host must stay valid (and should be pinned) until the matching collect() returns. */
+YB_API int yb_net_submit_host(yb_net* net, const float* img_host, int batch, const yb_detect_params* p, int* ticket);
+YB_API int yb_net_collect_host(yb_net* net, int ticket, int32_t* out_count, int32_t* out_class, int32_t* out_anchor,
+                               float* out_score, float* out_box, float* out_coef);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,3 +161,14 @@ def test_detect_host_end_to_end(cuda):
     for k in ('count', 'cls', 'anchor', 'score', 'box', 'coef'):
         assert np.array_equal(h[k], r[k].cpu().numpy()), k
     assert int(h['count'].min()) > 0
+    # pipelined submit/collect: two batches in flight, results identical to the synchronous call
+    eng = net.engine(2)
+    img2 = np.ascontiguousarray(img[::-1])
+    t0 = eng.submit_host(img, p)
+    t1 = eng.submit_host(img2, p)
+    with pytest.raises(_lib.YolactB200Error):
+        eng.submit_host(img, p)                                        # a third submission must be refused, not queued
+    a, b = eng.collect_host(t0), eng.collect_host(t1)
+    h2 = eng.detect_host(img2, p)
+    for k in ('count', 'cls', 'anchor', 'score', 'box', 'coef'):
+        assert np.array_equal(a[k], h[k]) and np.array_equal(b[k], h2[k]), k

@@ -64,6 +64,8 @@ PROTOTYPES = {
     'yb_conv2d': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp]),
     'yb_net_detect_host': (C.c_int, [vp, vp, C.c_int, C.POINTER(DetectParams), vp, vp, vp, vp, vp, vp]),
     'yb_net_last_proto': (vp, [vp]),
+    'yb_net_submit_host': (C.c_int, [vp, vp, C.c_int, C.POINTER(DetectParams), C.POINTER(C.c_int)]),
+    'yb_net_collect_host': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -89,6 +89,15 @@ struct yb_net {
   int32_t *d_cnt = nullptr, *d_ocls = nullptr, *d_oanc = nullptr; float *d_osc = nullptr, *d_obox = nullptr, *d_ocoef = nullptr;
   int host_batch = 0; int host_maxdet = 0;
   cudaStream_t own_stream = nullptr;
+  // pipelined host entry points: 2 slots of staging input + pinned result buffers
+  struct Slot {
+    float* d_stage = nullptr;                 // [B,3,S,S] staging copy target (copy stream)
+    void* h_res = nullptr;                    // pinned: count | class | anchor | score | box | coef
+    cudaEvent_t h2d = nullptr, done = nullptr;
+    int batch = 0, max_det = 0, busy = 0;
+  } slot[2];
+  cudaStream_t copy_stream = nullptr;
+  int next_ticket = 0;
   bool profiling = false;
   // CUDA graphs of (forward + post-process) for the host-buffer entry point, keyed by batch + params
   struct HostGraph { cudaGraphExec_t exec; uint64_t launches; };
@@ -488,6 +497,8 @@ extern "C" void yb_net_destroy(yb_net* net) {
                   (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
     cudaFree(p);
   net->drop_graphs();
+  for (auto& sl : net->slot) { cudaFree(sl.d_stage); if (sl.h_res) cudaFreeHost(sl.h_res); if (sl.h2d) cudaEventDestroy(sl.h2d); if (sl.done) cudaEventDestroy(sl.done); }
+  if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
   if (net->own_stream) cudaStreamDestroy(net->own_stream);
   delete net;
 }
@@ -773,76 +784,91 @@ extern "C" int yb_net_read_activation(yb_net* net, const char* name, int batch, 
 
 extern "C" const float* yb_net_last_proto(const yb_net* net) { return net ? net->d_proto : nullptr; }
 
+namespace {
+
+int ensure_host_scratch(yb_net* net, const yb_detect_params* p) {
+  const size_t B = net->max_batch, A = net->A, C = net->cfg.num_classes, K = net->cfg.coef_dim, S = net->cfg.img_size, P = net->P;
+  if (!net->own_stream) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&net->own_stream, cudaStreamNonBlocking));
+  if (net->host_batch == (int)B && net->host_maxdet >= p->max_det) return YB_OK;
+  net->drop_graphs();
+  for (void* q : {(void*)net->d_img, (void*)net->d_cls, (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws,
+                  (void*)net->d_cnt, (void*)net->d_ocls, (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
+    cudaFree(q);
+  YB_CHECK_CUDA(cudaMalloc(&net->d_img, B * 3 * S * S * 4));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_cls, B * A * C * 4));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_box, B * A * 16));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_coef, B * A * K * 4));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_proto, B * P * P * K * 4));
+  yb_detect_params pm = *p;
+  pm.top_k = 256; pm.max_det = 256;
+  net->ws_bytes = yb_detect_workspace_bytes((int)B, (int)A, &pm);
+  YB_CHECK_CUDA(cudaMalloc(&net->d_ws, net->ws_bytes));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_cnt, B * 4));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_ocls, B * 256 * 4));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_oanc, B * 256 * 4));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_osc, B * 256 * 4));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_obox, B * 256 * 16));
+  YB_CHECK_CUDA(cudaMalloc(&net->d_ocoef, B * 256 * K * 4));
+  net->host_batch = (int)B; net->host_maxdet = 256;
+  return YB_OK;
+}
+
+int check_host_call(yb_net* net, int batch, const yb_detect_params* p, const char* who) {
+  YB_REQUIRE(net->finalized, YB_ERR_STATE, "%s: call yb_net_finalize first", who);
+  YB_REQUIRE(batch >= 1 && batch <= net->max_batch, YB_ERR_INVALID, "%s: batch=%d outside [1,%d]", who, batch, net->max_batch);
+  YB_REQUIRE(p->num_classes == net->cfg.num_classes && p->coef_dim == net->cfg.coef_dim, YB_ERR_INVALID,
+             "%s: params do not match the network (classes %d/%d, coef %d/%d)", who, p->num_classes, net->cfg.num_classes, p->coef_dim,
+             net->cfg.coef_dim);
+  return YB_OK;
+}
+
+// forward + post-process of net->d_img on stream s (captured into a CUDA graph per (batch, params))
+int run_device_pipeline(yb_net* net, int batch, const yb_detect_params* p, bool want_coef, cudaStream_t s) {
+  auto run = [&]() -> int {
+    YB_PROPAGATE(yb_net_forward(net, net->d_img, batch, net->d_cls, net->d_box, net->d_coef, net->d_proto, s));
+    YB_PROPAGATE(yb_detect(net->d_cls, net->d_box, net->d_coef, net->d_anchors, batch, net->A, p, net->d_ws, net->ws_bytes, net->d_cnt,
+                           net->d_ocls, net->d_oanc, net->d_osc, net->d_obox, want_coef ? net->d_ocoef : nullptr, s));
+    return YB_OK;
+  };
+  if (net->profiling || getenv("YOLACT_B200_NO_GRAPH")) return run();
+  // ~150 kernel launches per call: capture once per (batch, params), replay afterwards
+  std::string key((const char*)p, sizeof(*p));
+  key += std::to_string(batch) + (want_coef ? "c" : "n");
+  auto it = net->host_graphs.find(key);
+  if (it == net->host_graphs.end()) {
+    YB_PROPAGATE(run());                                         // warm run: lazy one-time setup stays outside the capture
+    YB_CHECK_CUDA(cudaStreamSynchronize(s));
+    const uint64_t l0 = g_launches.load();
+    YB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int st = run();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (st != YB_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+    YB_CHECK_CUDA(ce);
+    yb_net::HostGraph hg{nullptr, g_launches.load() - l0};
+    ce = cudaGraphInstantiate(&hg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    YB_CHECK_CUDA(ce);
+    it = net->host_graphs.emplace(key, hg).first;
+  }
+  YB_CHECK_CUDA(cudaGraphLaunch(it->second.exec, s));
+  count_launch(it->second.launches);
+  return YB_OK;
+}
+
+}  // namespace
+
 extern "C" int yb_net_detect_host(yb_net* net, const float* img_host, int batch, const yb_detect_params* p,
                                   int32_t* out_count, int32_t* out_class, int32_t* out_anchor, float* out_score,
                                   float* out_box, float* out_coef) {
   YB_REQUIRE(net && img_host && p && out_count && out_class && out_anchor && out_score && out_box, YB_ERR_INVALID,
              "yb_net_detect_host: NULL argument");
-  YB_REQUIRE(net->finalized, YB_ERR_STATE, "yb_net_detect_host: call yb_net_finalize first");
-  YB_REQUIRE(batch >= 1 && batch <= net->max_batch, YB_ERR_INVALID, "yb_net_detect_host: batch=%d outside [1,%d]", batch, net->max_batch);
-  YB_REQUIRE(p->num_classes == net->cfg.num_classes && p->coef_dim == net->cfg.coef_dim, YB_ERR_INVALID,
-             "yb_net_detect_host: params do not match the network (classes %d/%d, coef %d/%d)", p->num_classes,
-             net->cfg.num_classes, p->coef_dim, net->cfg.coef_dim);
-  const size_t B = net->max_batch, A = net->A, C = net->cfg.num_classes, K = net->cfg.coef_dim, S = net->cfg.img_size, P = net->P;
-  const size_t D = p->max_det;
-  if (!net->own_stream) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&net->own_stream, cudaStreamNonBlocking));
-  if (net->host_batch != (int)B || net->host_maxdet < (int)D) {
-    net->drop_graphs();
-    for (void* q : {(void*)net->d_img, (void*)net->d_cls, (void*)net->d_box, (void*)net->d_coef, (void*)net->d_proto, net->d_ws,
-                    (void*)net->d_cnt, (void*)net->d_ocls, (void*)net->d_oanc, (void*)net->d_osc, (void*)net->d_obox, (void*)net->d_ocoef})
-      cudaFree(q);
-    YB_CHECK_CUDA(cudaMalloc(&net->d_img, B * 3 * S * S * 4));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_cls, B * A * C * 4));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_box, B * A * 16));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_coef, B * A * K * 4));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_proto, B * P * P * K * 4));
-    yb_detect_params pm = *p;
-    pm.top_k = 256; pm.max_det = 256;
-    net->ws_bytes = yb_detect_workspace_bytes((int)B, (int)A, &pm);
-    YB_CHECK_CUDA(cudaMalloc(&net->d_ws, net->ws_bytes));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_cnt, B * 4));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_ocls, B * 256 * 4));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_oanc, B * 256 * 4));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_osc, B * 256 * 4));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_obox, B * 256 * 16));
-    YB_CHECK_CUDA(cudaMalloc(&net->d_ocoef, B * 256 * K * 4));
-    net->host_batch = (int)B; net->host_maxdet = 256;
-  }
+  YB_PROPAGATE(check_host_call(net, batch, p, "yb_net_detect_host"));
+  YB_PROPAGATE(ensure_host_scratch(net, p));
+  const size_t K = net->cfg.coef_dim, S = net->cfg.img_size, D = p->max_det, b = batch;
   cudaStream_t s = net->own_stream;
-  const size_t b = batch;
   YB_CHECK_CUDA(cudaMemcpyAsync(net->d_img, img_host, b * 3 * S * S * 4, cudaMemcpyHostToDevice, s));
-  auto run = [&]() -> int {
-    YB_PROPAGATE(yb_net_forward(net, net->d_img, batch, net->d_cls, net->d_box, net->d_coef, net->d_proto, s));
-    YB_PROPAGATE(yb_detect(net->d_cls, net->d_box, net->d_coef, net->d_anchors, batch, (int)A, p, net->d_ws, net->ws_bytes, net->d_cnt,
-                           net->d_ocls, net->d_oanc, net->d_osc, net->d_obox, out_coef ? net->d_ocoef : nullptr, s));
-    return YB_OK;
-  };
-  if (net->profiling || getenv("YOLACT_B200_NO_GRAPH")) {
-    YB_PROPAGATE(run());
-  } else {
-    // ~150 kernel launches per call: capture once per (batch, params), replay afterwards
-    std::string key((const char*)p, sizeof(*p));
-    key += std::to_string(batch) + (out_coef ? "c" : "n");
-    auto it = net->host_graphs.find(key);
-    if (it == net->host_graphs.end()) {
-      YB_PROPAGATE(run());                                         // warm run: lazy one-time setup stays outside the capture
-      YB_CHECK_CUDA(cudaStreamSynchronize(s));
-      const uint64_t l0 = g_launches.load();
-      YB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      const int st = run();
-      cudaGraph_t graph = nullptr;
-      cudaError_t ce = cudaStreamEndCapture(s, &graph);
-      if (st != YB_OK) { if (graph) cudaGraphDestroy(graph); return st; }
-      YB_CHECK_CUDA(ce);
-      yb_net::HostGraph hg{nullptr, g_launches.load() - l0};
-      ce = cudaGraphInstantiate(&hg.exec, graph, 0);
-      cudaGraphDestroy(graph);
-      YB_CHECK_CUDA(ce);
-      it = net->host_graphs.emplace(key, hg).first;
-    }
-    YB_CHECK_CUDA(cudaGraphLaunch(it->second.exec, s));
-    count_launch(it->second.launches);
-  }
+  YB_PROPAGATE(run_device_pipeline(net, batch, p, out_coef != nullptr, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_count, net->d_cnt, b * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_class, net->d_ocls, b * D * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_anchor, net->d_oanc, b * D * 4, cudaMemcpyDeviceToHost, s));
@@ -850,6 +876,61 @@ extern "C" int yb_net_detect_host(yb_net* net, const float* img_host, int batch,
   YB_CHECK_CUDA(cudaMemcpyAsync(out_box, net->d_obox, b * D * 16, cudaMemcpyDeviceToHost, s));
   if (out_coef) YB_CHECK_CUDA(cudaMemcpyAsync(out_coef, net->d_ocoef, b * D * K * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaStreamSynchronize(s));
+  return YB_OK;
+}
+
+extern "C" int yb_net_submit_host(yb_net* net, const float* img_host, int batch, const yb_detect_params* p, int* ticket) {
+  YB_REQUIRE(net && img_host && p && ticket, YB_ERR_INVALID, "yb_net_submit_host: NULL argument");
+  YB_PROPAGATE(check_host_call(net, batch, p, "yb_net_submit_host"));
+  YB_PROPAGATE(ensure_host_scratch(net, p));
+  const size_t K = net->cfg.coef_dim, S = net->cfg.img_size, D = p->max_det, b = batch, B = net->max_batch;
+  if (!net->copy_stream) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking));
+  const int t = net->next_ticket;
+  yb_net::Slot& sl = net->slot[t & 1];
+  YB_REQUIRE(!sl.busy, YB_ERR_STATE, "yb_net_submit_host: two submissions already in flight (collect ticket %d first)", t - 2);
+  if (!sl.d_stage) {
+    YB_CHECK_CUDA(cudaMalloc(&sl.d_stage, B * 3 * S * S * 4));
+    YB_CHECK_CUDA(cudaMallocHost(&sl.h_res, B * (4 + 256 * (4 + 4 + 4 + 16 + K * 4))));
+    YB_CHECK_CUDA(cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+    YB_CHECK_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  // copy stream: H2D into the slot's staging buffer (overlaps the previous submission's compute)
+  YB_CHECK_CUDA(cudaMemcpyAsync(sl.d_stage, img_host, b * 3 * S * S * 4, cudaMemcpyHostToDevice, net->copy_stream));
+  YB_CHECK_CUDA(cudaEventRecord(sl.h2d, net->copy_stream));
+  cudaStream_t s = net->own_stream;
+  YB_CHECK_CUDA(cudaStreamWaitEvent(s, sl.h2d, 0));
+  YB_CHECK_CUDA(cudaMemcpyAsync(net->d_img, sl.d_stage, b * 3 * S * S * 4, cudaMemcpyDeviceToDevice, s));
+  YB_PROPAGATE(run_device_pipeline(net, batch, p, true, s));
+  char* h = (char*)sl.h_res;
+  YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_cnt, b * 4, cudaMemcpyDeviceToHost, s)); h += B * 4;
+  YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_ocls, b * D * 4, cudaMemcpyDeviceToHost, s)); h += B * 256 * 4;
+  YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_oanc, b * D * 4, cudaMemcpyDeviceToHost, s)); h += B * 256 * 4;
+  YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_osc, b * D * 4, cudaMemcpyDeviceToHost, s)); h += B * 256 * 4;
+  YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_obox, b * D * 16, cudaMemcpyDeviceToHost, s)); h += B * 256 * 16;
+  YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_ocoef, b * D * K * 4, cudaMemcpyDeviceToHost, s));
+  YB_CHECK_CUDA(cudaEventRecord(sl.done, s));
+  sl.batch = batch; sl.max_det = (int)D; sl.busy = 1;
+  *ticket = t;
+  net->next_ticket = t + 1;
+  return YB_OK;
+}
+
+extern "C" int yb_net_collect_host(yb_net* net, int ticket, int32_t* out_count, int32_t* out_class, int32_t* out_anchor,
+                                   float* out_score, float* out_box, float* out_coef) {
+  YB_REQUIRE(net && out_count && out_class && out_anchor && out_score && out_box, YB_ERR_INVALID, "yb_net_collect_host: NULL argument");
+  YB_REQUIRE(ticket >= 0 && ticket < net->next_ticket && ticket >= net->next_ticket - 2, YB_ERR_INVALID, "yb_net_collect_host: bad ticket %d", ticket);
+  yb_net::Slot& sl = net->slot[ticket & 1];
+  YB_REQUIRE(sl.busy, YB_ERR_STATE, "yb_net_collect_host: ticket %d already collected", ticket);
+  YB_CHECK_CUDA(cudaEventSynchronize(sl.done));
+  const size_t K = net->cfg.coef_dim, D = sl.max_det, b = sl.batch, B = net->max_batch;
+  const char* h = (const char*)sl.h_res;
+  memcpy(out_count, h, b * 4); h += B * 4;
+  memcpy(out_class, h, b * D * 4); h += B * 256 * 4;
+  memcpy(out_anchor, h, b * D * 4); h += B * 256 * 4;
+  memcpy(out_score, h, b * D * 4); h += B * 256 * 4;
+  memcpy(out_box, h, b * D * 16); h += B * 256 * 16;
+  if (out_coef) memcpy(out_coef, h, b * D * K * 4);
+  sl.busy = 0;
   return YB_OK;
 }
 

@@ -122,6 +122,27 @@ class Engine:
         _lib.check(self.L.yb_net_anchors_host(self.h, a.ctypes.data), 'yb_net_anchors_host')
         return a
 
+    def submit_host(self, img_host, params):
+        """Pipelined end-to-end call (yb_net_submit_host): returns a ticket; the H2D copy of this batch
+        overlaps the compute of the previous one.  img_host must be a contiguous float32 array that
+        stays alive (ideally pinned) until collect_host(ticket)."""
+        t = ctypes.c_int()
+        _lib.check(self.L.yb_net_submit_host(self.h, img_host.ctypes.data, img_host.shape[0], ctypes.byref(params), ctypes.byref(t)),
+                   'yb_net_submit_host')
+        self._pending = getattr(self, '_pending', {})
+        self._pending[t.value] = (img_host, img_host.shape[0], params.max_det)
+        return t.value
+
+    def collect_host(self, ticket):
+        _, B, D = self._pending.pop(ticket)
+        K = self.cfg.coef_dim
+        out = dict(count=np.zeros(B, np.int32), cls=np.zeros((B, D), np.int32), anchor=np.zeros((B, D), np.int32),
+                   score=np.zeros((B, D), np.float32), box=np.zeros((B, D, 4), np.float32), coef=np.zeros((B, D, K), np.float32))
+        _lib.check(self.L.yb_net_collect_host(self.h, ticket, out['count'].ctypes.data, out['cls'].ctypes.data, out['anchor'].ctypes.data,
+                                              out['score'].ctypes.data, out['box'].ctypes.data, out['coef'].ctypes.data),
+                   'yb_net_collect_host')
+        return out
+
     def detect_host(self, img_host, params):
         """End to end with host buffers (yb_net_detect_host): numpy in, numpy out."""
         img = np.ascontiguousarray(img_host, dtype=np.float32)
