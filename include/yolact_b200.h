@@ -112,6 +112,13 @@ YB_API int yb_mask_assemble(const float* proto, const float* coef, const float* 
                      void* out_mask, int32_t* out_box_px, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Pre-process -- replaces utils/augmentations.py:219-227 val_aug(img, val_size):
+ * uint8 BGR HWC image [h,w,3] (device) -> float32 RGB CHW [3,S,S] (device): pad to square at the
+ * top-left with the BGR mean, bilinear resize (OpenCV INTER_LINEAR coordinates), (x-mean)/std.
+ * ---------------------------------------------------------------------------------------- */
+YB_API int yb_val_aug(const uint8_t* img_bgr, int h, int w, int img_size, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Network: ResNet-50/101 + FPN + ProtoNet + prediction heads (modules/resnet.py,
  * modules/yolact.py:12-164), eval forward.  Weights are handed over by their reference
  * state-dict names; BatchNorm is folded at finalize time.

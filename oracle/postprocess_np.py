@@ -275,3 +275,44 @@ def after_nms(class_ids, scores, boxes, coefs, proto, img_h, img_w, visual_thre=
     if return_soft:
         return class_ids, scores, boxes_px, hard, soft
     return class_ids, scores, boxes_px, hard
+
+
+# ----------------------------------------------------------------------------- val_aug (pre-process)
+NORM_MEAN = np.array([103.94, 116.78, 123.68], dtype=F32)     # BGR, config.py:66
+NORM_STD = np.array([57.38, 57.12, 58.40], dtype=F32)         # config.py:67
+
+
+def _cv_linear_axis(src_size, dst_size):
+    """OpenCV resize (INTER_LINEAR, float path) coordinate tables: fx = (dx+0.5)*scale-0.5 in double
+    rounded to float, sx = floor(fx); clamped at both borders with weight 0 on the outside tap."""
+    scale = float(src_size) / float(dst_size)
+    d = np.arange(dst_size, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(F32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(F32)).astype(F32)
+    lo = s < 0
+    s[lo] = 0; f[lo] = 0
+    hi = s >= src_size - 1
+    s[hi] = src_size - 1; f[hi] = 0
+    s1 = np.minimum(s + 1, src_size - 1)
+    return s, s1, (F32(1) - f).astype(F32), f
+
+
+def val_aug(img_bgr_u8, val_size):
+    """utils/augmentations.py:219-227: float32 -> pad to square (top-left, mean fill, :138-165) ->
+    cv2.resize bilinear (:168-189) -> (x - mean) / std, BGR->RGB, HWC->CHW (:212-216)."""
+    img = img_bgr_u8.astype(F32)
+    h, w = img.shape[:2]
+    P = max(h, w)
+    if h != w:
+        pad = np.empty((P, P, 3), dtype=F32)
+        pad[:] = NORM_MEAN
+        pad[:h, :w] = img
+        img = pad
+    x0, x1, ax0, ax1 = _cv_linear_axis(P, val_size)
+    y0, y1, ay0, ay1 = _cv_linear_axis(P, val_size)
+    rows0 = img[y0][:, x0] * ax0[None, :, None] + img[y0][:, x1] * ax1[None, :, None]
+    rows1 = img[y1][:, x0] * ax0[None, :, None] + img[y1][:, x1] * ax1[None, :, None]
+    out = (rows0 * ay0[:, None, None] + rows1 * ay1[:, None, None]).astype(F32)
+    out = (out - NORM_MEAN) / NORM_STD
+    return np.ascontiguousarray(out[:, :, ::-1].transpose(2, 0, 1)).astype(F32)

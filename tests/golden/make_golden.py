@@ -247,15 +247,36 @@ def gen_forward(rcfg, ryolact):
     np.savez_compressed(os.path.join(HERE, 'forward.npz'), **out)
 
 
+def gen_val_aug():
+    """Pre-process goldens from the reference's own val_aug (cv2)."""
+    sys.path.insert(0, REF)
+    from utils.augmentations import val_aug as ref_val_aug
+    out = {}
+    for name, h, w, S, seed in (('97x64_S96', 97, 64, 96, 1), ('120x160_S128', 120, 160, 128, 2), ('200x200_S64', 200, 200, 64, 3),
+                                ('375x500_S550', 375, 500, 550, 4)):
+        img = (synth.uniform(seed, 21, (h, w, 3)) * 256).astype(np.uint8)
+        ref = ref_val_aug(img, S).astype(np.float32)
+        mine = pp.val_aug(img, S)
+        err = float(np.abs(ref - mine).max())
+        assert err < 2e-4, (name, err)      # cv2's (IPP) float resize differs from the textbook formula by ~1e-4
+        sub = 1 if S <= 128 else 11
+        out[name + '/sub'] = np.int64(sub)
+        out[name + '/out'] = ref[:, ::sub, ::sub]
+        out[name + '/sum'] = ref.astype(np.float64).sum(axis=(1, 2))
+        print(f'  val_aug {name}: oracle-vs-reference max err {err:.2e}')
+    np.savez_compressed(os.path.join(HERE, 'val_aug.npz'), **out)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     build_cython_nms()
     rcfg, ryolact, rout, rbox = import_reference()
-    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward']
+    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug']
     if 'anchors' in which: gen_anchors(rcfg, ryolact)
     if 'hard' in which: gen_hard_nms()
     if 'post' in which: gen_postprocess(rcfg, rout)
     if 'after' in which: gen_after_nms(rcfg, rout)
     if 'forward' in which: gen_forward(rcfg, ryolact)
+    if 'valaug' in which: gen_val_aug()
     print('done')

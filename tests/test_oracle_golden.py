@@ -100,3 +100,20 @@ def test_c_hard_nms_matches_numpy_oracle_and_golden():
             assert kept == len(idx)
             assert np.array_equal(idx, g[f's{seed}_n{n}_t{thr}'])
             assert np.array_equal(idx, pp.hard_nms(dets, thr))
+
+
+VAL_AUG_CASES = (('97x64_S96', 97, 64, 96, 1), ('120x160_S128', 120, 160, 128, 2), ('200x200_S64', 200, 200, 64, 3),
+                 ('375x500_S550', 375, 500, 550, 4))
+
+
+def test_val_aug_golden():
+    """numpy restatement of val_aug vs the reference's cv2 pipeline (cv2's IPP resize differs from the
+    textbook bilinear formula by ~1e-4 on normalised values)."""
+    g = load_golden('val_aug.npz')
+    for name, h, w, S, seed in VAL_AUG_CASES:
+        img = (synth.uniform(seed, 21, (h, w, 3)) * 256).astype(np.uint8)
+        out = pp.val_aug(img, S)
+        sub = int(g[name + '/sub'])
+        assert out.shape == (3, S, S)
+        assert np.abs(out[:, ::sub, ::sub] - g[name + '/out']).max() < 2e-4
+        assert np.allclose(out.astype(np.float64).sum(axis=(1, 2)), g[name + '/sum'], rtol=0, atol=0.05)

@@ -213,3 +213,18 @@ def test_reference_signature_nms_after_nms(cuda):
     r = nms(t(cls0)[None], t(box)[None], t(coef)[None], t(proto)[None], t(anchors), cfg)
     assert r == (None,) * 5
     assert after_nms(None, None, None, None, None, 10, 10) == (None,) * 4
+
+
+def test_val_aug_gpu(cuda):
+    """GPU pre-process (yb_val_aug) vs the oracle and the reference-minted goldens."""
+    from yolact_minimal_b200.utils.augmentations import val_aug
+    from test_oracle_golden import VAL_AUG_CASES
+    g = load_golden('val_aug.npz')
+    for name, h, w, S, seed in VAL_AUG_CASES:
+        img = (synth.uniform(seed, 21, (h, w, 3)) * 256).astype(np.uint8)
+        out = val_aug(img, S).cpu().numpy()
+        ref = pp.val_aug(img, S)
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() < 2e-5, np.abs(out - ref).max()           # same formula, fp32
+        sub = int(g[name + '/sub'])
+        assert np.abs(out[:, ::sub, ::sub] - g[name + '/out']).max() < 2e-4      # vs cv2 (IPP)

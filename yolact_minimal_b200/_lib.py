@@ -46,6 +46,7 @@ PROTOTYPES = {
     'yb_mask_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'yb_mask_assemble': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    vp, C.c_size_t, vp, vp, vp]),
+    'yb_val_aug': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     'yb_net_create': (C.c_int, [C.POINTER(NetConfig), C.POINTER(vp)]),
     'yb_net_destroy': (None, [vp]),
     'yb_net_num_params': (C.c_int, [vp]),

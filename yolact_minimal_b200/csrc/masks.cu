@@ -137,3 +137,47 @@ extern "C" int yb_mask_assemble(const float* proto, const float* coef, const flo
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
+
+// ================================================================================================
+// Pre-process: the reference's val_aug on the GPU --
+// utils/augmentations.py:219-227: uint8 BGR HWC -> float32, pad to square at the top-left with the
+// BGR mean (:138-165), bilinear resize to S x S with OpenCV's INTER_LINEAR coordinate rule
+// (fx = (dx+0.5)*scale-0.5, clamped taps), (x-mean)/std, BGR->RGB, CHW (:212-216).  One kernel,
+// one read of the uint8 image, one write of the network input (4x less H2D than fp32 images).
+// ================================================================================================
+namespace yb {
+__global__ void __launch_bounds__(256) k_val_aug(const uint8_t* __restrict__ img, int h, int w, int S, float* __restrict__ out) {
+  const int P = h > w ? h : w;
+  const double scale = (double)P / (double)S;
+  const float mean[3] = {103.94f, 116.78f, 123.68f}, stdv[3] = {57.38f, 57.12f, 58.40f};
+  const int total = S * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int dy = i / S, dx = i - dy * S;
+    float fx = (float)(((double)dx + 0.5) * scale - 0.5), fy = (float)(((double)dy + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx), sy = (int)floorf(fy);
+    fx -= (float)sx; fy -= (float)sy;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= P - 1) { sx = P - 1; fx = 0.f; }
+    if (sy < 0) { sy = 0; fy = 0.f; }
+    if (sy >= P - 1) { sy = P - 1; fy = 0.f; }
+    const int sx1 = min(sx + 1, P - 1), sy1 = min(sy + 1, P - 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                      // c indexes BGR; output channel is 2 - c (RGB)
+      auto px = [&](int y, int x) -> float { return (y < h && x < w) ? (float)img[((size_t)y * w + x) * 3 + c] : mean[c]; };
+      const float r0 = px(sy, sx) * (1.f - fx) + px(sy, sx1) * fx;
+      const float r1 = px(sy1, sx) * (1.f - fx) + px(sy1, sx1) * fx;
+      const float v = r0 * (1.f - fy) + r1 * fy;
+      out[(size_t)(2 - c) * total + i] = (v - mean[c]) / stdv[c];
+    }
+  }
+}
+}  // namespace yb
+
+extern "C" int yb_val_aug(const uint8_t* img_bgr, int h, int w, int img_size, float* out, void* stream) {
+  YB_REQUIRE(img_bgr && out, YB_ERR_INVALID, "yb_val_aug: NULL pointer argument");
+  YB_REQUIRE(h > 0 && w > 0 && img_size > 0 && img_size <= 8192, YB_ERR_INVALID, "yb_val_aug: h=%d w=%d img_size=%d", h, w, img_size);
+  const int total = img_size * img_size;
+  yb::k_val_aug<<<yb::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(img_bgr, h, w, img_size, out);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
