@@ -289,8 +289,36 @@ def run_ours(args):
                                             np.array_equal(det1['cls'][0, :d].cpu().numpy(), o[0]) and
                                             np.array_equal(det1['anchor'][0, :d].cpu().numpy(), o[3]))
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------
-    tc = prof['conv_tc'] if prof['conv_tc']['launches'] else prof['conv_simt']
+    # ---- the same step with bf16 operands (same kernels, same speed class; 8-bit mantissa) -----------------
+    other = None
+    if args.precision == 'fp16' and not os.environ.get('YB_BENCH_SKIP_BF16'):
+        del net, eng
+        torch.cuda.empty_cache()
+        cfg2 = make_config(ARCH + '_coco', IMG)
+        cfg2.precision, cfg2.max_batch = 'bf16', BATCH
+        net2 = Yolact(cfg2)
+        net2.load_state_dict(ft.synth_state_dict(ARCH, seed=0), strict=True)
+        net2 = net2.to(dev).eval()
+
+        def step2(i):
+            with torch.no_grad():
+                c_, b_, k_, _ = net2(imgs[i & 1])
+            return detect_batched(c_, b_, k_, anchors, cfg2)
+        for i in range(3):
+            step2(i)
+        torch.cuda.synchronize()
+        a_, b2_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for i in range(10):
+            step2(i)
+        b2_.record(); torch.cuda.synchronize()
+        with torch.no_grad():
+            m2 = [o[:1].cpu().numpy() for o in net2(imgs[0][:1])]
+        other = {'dtype': 'bf16 operands, f32 accumulate', 'value_single_rank': BATCH * 10 / (a_.elapsed_time(b2_) / 1e3), 'steps': 10,
+                 'parity_vs_fp32_oracle_max_abs_err': {n: float(np.abs(m - r).max()) for n, m, r in zip(('cls', 'box', 'coef', 'proto'), m2, ref)}}
+        eng = net2.engine(BATCH)
+
+    # ---- roofline of the dominant kernel ----    tc = prof['conv_tc'] if prof['conv_tc']['launches'] else prof['conv_simt']
     dom = 'k_conv_tc' if prof['conv_tc']['launches'] else 'k_conv_simt'
     achieved = tc['flops'] / (tc['ms'] * 1e-3) / 1e12 if tc['ms'] else 0.0
     total_ms = sum(v['ms'] for v in prof.values())
@@ -329,7 +357,8 @@ def run_ours(args):
             'cpu_baseline': {'value': cpu_v, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
                              'sample': f'8 reps x 4 images ({cpu_s:.1f} s): torch fp32 CPU forward + numpy nms()',
                              'fast_nms_us_per_img': cpu_nms_us},
-            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_fp32_oracle_max_abs_err': parity}
+            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_fp32_oracle_max_abs_err': parity,
+            'bf16_arm': other}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -4,6 +4,7 @@
 // kernels, with the residual adds in their epilogues.
 #include "layers.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace yb {
@@ -201,41 +202,74 @@ int launch_layernorm(const void* in, void* out, const float* g, const float* be,
 // PatchMerging gather + LayerNorm(4C) (modules/swin_transformer.py:299-325): output token (y,x)
 // concatenates input tokens (2y,2x), (2y+1,2x), (2y,2x+1), (2y+1,2x+1) (zero beyond an odd edge).
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256) k_patch_merge_ln(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ g,
                                                         const float* __restrict__ be, int B, int C, int Hin, int Hout) {
+  constexpr int N = TokVec<T>::N;
   const int lane = threadIdx.x & 31;
-  const int Hpi = Hin + 2, Hpo = Hout + 2, C4 = 4 * C;
+  const int Hpi = Hin + 2, Hpo = Hout + 2, C4 = 4 * C, nvec = C4 / N, vpp = C / N;     // vectors per source token
   const long long total = (long long)B * Hpo * Hpo;
   for (long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tok < total; tok += (long long)gridDim.x * 8) {
     const int xp = (int)(tok % Hpo), yp = (int)((tok / Hpo) % Hpo), b = (int)(tok / ((long long)Hpo * Hpo));
     T* o = out + tok * C4;
-    if (yp == 0 || yp == Hout + 1 || xp == 0 || xp == Hout + 1) {
-      for (int c = lane; c < C4; c += 32) tok_st<T>(o + c, 0.f);
-      continue;
-    }
+    const bool halo = yp == 0 || yp == Hout + 1 || xp == 0 || xp == Hout + 1;
     const int y = yp - 1, x = xp - 1;
-    auto src = [&](int c4) -> float {
-      const int part = c4 / C, c = c4 - part * C;
-      const int iy = 2 * y + (part & 1), ix = 2 * x + (part >> 1);
-      if (iy >= Hin || ix >= Hin) return 0.f;
-      return Tok<T>::ld(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + c);
-    };
+    float buf[NV][N];
     float s = 0.f;
-    for (int c = lane; c < C4; c += 32) s += src(c);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      bool have = false;
+      if (v < nvec && !halo) {
+        const int part = v / vpp, cv = v - part * vpp;
+        const int iy = 2 * y + (part & 1), ix = 2 * x + (part >> 1);
+        if (iy < Hin && ix < Hin) { TokVec<T>::ld(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + cv * N, buf[i]); have = true; }
+      }
+      if (!have) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) buf[i][e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < N; ++e) s += buf[i][e];
+    }
     const float mean = warp_sum(s) / (float)C4;
-    float v = 0.f;
-    for (int c = lane; c < C4; c += 32) { const float d = src(c) - mean; v += d * d; }
-    const float rstd = rsqrtf(warp_sum(v) / (float)C4 + 1e-5f);
-    for (int c = lane; c < C4; c += 32) tok_st<T>(o + c, (src(c) - mean) * rstd * g[c] + be[c]);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) { const float d = buf[i][e] - mean; var += d * d; }
+      }
+    const float rstd = rsqrtf(warp_sum(var) / (float)C4 + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float r[N];
+#pragma unroll
+        for (int e = 0; e < N; ++e) r[e] = halo ? 0.f : (buf[i][e] - mean) * rstd * __ldg(g + v * N + e) + __ldg(be + v * N + e);
+        TokVec<T>::st(o + v * N, r);
+      }
+    }
   }
+}
+
+template <typename T>
+static void patch_merge_dispatch(const T* in, T* out, const float* g, const float* be, int B, int C, int Hin, int Hout, int nvec, int blocks,
+                                 cudaStream_t s) {
+  if (nvec <= 64) k_patch_merge_ln<T, 2><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, Hin, Hout);
+  else if (nvec <= 96) k_patch_merge_ln<T, 3><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, Hin, Hout);
+  else if (nvec <= 192) k_patch_merge_ln<T, 6><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, Hin, Hout);
+  else k_patch_merge_ln<T, 12><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, Hin, Hout);
 }
 
 int launch_patch_merge_ln(const void* in, void* out, const float* g, const float* be, int dt, int B, int C, int Hin, int Hout,
                           cudaStream_t s) {
+  const int N = dt == DT_F32 ? 4 : 8, nvec = 4 * C / N;
+  YB_REQUIRE(C % N == 0 && nvec <= 384, YB_ERR_UNSUPPORTED, "patch_merge_ln: C=%d", C);
   const long long total = (long long)B * (Hout + 2) * (Hout + 2);
   const int blocks = (int)std::min<long long>((total + 7) / 8, 148LL * 16);
-  YB_DISPATCH_DT(dt, (k_patch_merge_ln<T><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, g, be, B, C, Hin, Hout)));
+  YB_DISPATCH_DT(dt, (patch_merge_dispatch<T>((const T*)in, (T*)out, g, be, B, C, Hin, Hout, nvec, blocks, s)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -332,10 +366,205 @@ __global__ void __launch_bounds__(64) k_window_attention(const T* __restrict__ q
   for (int d = 0; d < HD; d += TokVec<T>::N) TokVec<T>::st(op + d, o + d);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core window attention for the 16-bit modes: one WARP per (window, head), 49 tokens padded to
+// 64.  S = Q K^T and O = P V run on mma.sync m16n8k16 (fp32 accumulate) with the flash-attention
+// register trick: the score accumulators of two adjacent 8-column tiles ARE the A fragment of the
+// P.V product, so probabilities never leave registers.  Scale, relative-position bias, shift mask and
+// softmax are applied to the fp32 accumulators.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Mma16;
+template <> struct Mma16<__half> {
+  static __device__ __forceinline__ void mma(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float x, float y) { __half2 v = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&v); }
+  static __device__ __forceinline__ __half from_f(float x) { return __float2half_rn(x); }
+};
+template <> struct Mma16<__nv_bfloat16> {
+  static __device__ __forceinline__ void mma(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float x, float y) { __nv_bfloat162 v = __floats2bfloat162_rn(x, y); return *reinterpret_cast<uint32_t*>(&v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float x) { return __float2bfloat16_rn(x); }
+};
+
+constexpr int TCA_WARPS = 4;
+constexpr int QK_LD = 40;      // halves per Q/K row (32 + 8 pad: conflict-free fragment loads)
+constexpr int VT_LD = 72;      // halves per V^T row (64 + 8 pad)
+
+template <typename T>
+struct __align__(16) AttnSmem {
+  T q[64][QK_LD];
+  T k[64][QK_LD];
+  T vt[HD][VT_LD];
+  float tab[176];
+  int row[64];
+  int reg[64];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TCA_WARPS * 32) k_window_attention_tc(const T* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                                                                          const float* __restrict__ table, T* __restrict__ out, int B,
+                                                                          int H, int C, int nH, int shift) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  AttnSmem<T>& sm = reinterpret_cast<AttnSmem<T>*>(smem_raw)[warp];
+  const int Hpad = (H + WS - 1) / WS * WS, nW = Hpad / WS;
+  const long long units = (long long)B * nW * nW * nH;
+  const long long unit = (long long)blockIdx.x * TCA_WARPS + warp;
+  if (unit >= units) return;
+  const int head = (int)(unit % nH);
+  const int win = (int)((unit / nH) % (nW * nW));
+  const int b = (int)(unit / ((long long)nH * nW * nW));
+  const int wy = win / nW, wx = win - wy * nW;
+  const int Hp = H + 2, C3 = 3 * C;
+
+  for (int t = lane; t < 64; t += 32) {
+    int row = -2, reg = 0;                                          // -2: tile padding (t >= 49)
+    if (t < WT) {
+      const int iy = t / WS, ix = t - iy * WS;
+      const int ys = wy * WS + iy, xs = wx * WS + ix;
+      const int yo = (ys + shift) % Hpad, xo = (xs + shift) % Hpad;
+      row = (yo < H && xo < H) ? ((b * Hp + yo + 1) * Hp + xo + 1) : -1;   // -1: grid padding token (qkv == bias)
+      const int ry = ys < Hpad - WS ? 0 : (ys < Hpad - shift ? 1 : 2), rx = xs < Hpad - WS ? 0 : (xs < Hpad - shift ? 1 : 2);
+      reg = ry * 3 + rx;
+    }
+    sm.row[t] = row; sm.reg[t] = reg;
+  }
+  for (int i = lane; i < 169; i += 32) sm.tab[i] = __ldg(table + i * nH + head);
+  __syncwarp();
+  // Q, K (row-major) and V^T into shared memory
+  for (int idx = lane; idx < 64 * 4; idx += 32) {
+    const int t = idx >> 2, v8 = (idx & 3) * 8;
+    const int row = sm.row[t];
+    T qv[8], kv[8], vv[8];
+    if (row >= 0) {
+      const T* base = qkv + (size_t)row * C3 + head * HD + v8;
+      *reinterpret_cast<uint4*>(qv) = *reinterpret_cast<const uint4*>(base);
+      *reinterpret_cast<uint4*>(kv) = *reinterpret_cast<const uint4*>(base + C);
+      *reinterpret_cast<uint4*>(vv) = *reinterpret_cast<const uint4*>(base + 2 * C);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = head * HD + v8 + e;
+        qv[e] = Mma16<T>::from_f(row == -1 ? qkv_bias[c] : 0.f);
+        kv[e] = Mma16<T>::from_f(row == -1 ? qkv_bias[C + c] : 0.f);
+        vv[e] = Mma16<T>::from_f(row == -1 ? qkv_bias[2 * C + c] : 0.f);
+      }
+    }
+    *reinterpret_cast<uint4*>(&sm.q[t][v8]) = *reinterpret_cast<uint4*>(qv);
+    *reinterpret_cast<uint4*>(&sm.k[t][v8]) = *reinterpret_cast<uint4*>(kv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm.vt[v8 + e][t] = vv[e];
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, q4 = lane & 3;
+  const float scale = 0.17677669529663687f;
+  // the lane's 16 key columns: j = 8*nt + 2*q4 + e
+  for (int mt = 0; mt < 4; ++mt) {
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(&sm.q[16 * mt + g][16 * ks + 2 * q4]);
+      a[1] = *reinterpret_cast<const uint32_t*>(&sm.q[16 * mt + g + 8][16 * ks + 2 * q4]);
+      a[2] = *reinterpret_cast<const uint32_t*>(&sm.q[16 * mt + g][16 * ks + 8 + 2 * q4]);
+      a[3] = *reinterpret_cast<const uint32_t*>(&sm.q[16 * mt + g + 8][16 * ks + 8 + 2 * q4]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sm.k[8 * nt + g][16 * ks + 2 * q4]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sm.k[8 * nt + g][16 * ks + 8 + 2 * q4]);
+        Mma16<T>::mma(acc[nt], a, b0, b1);
+      }
+    }
+    // scores -> probabilities for rows i0 = 16mt+g and i1 = i0+8
+    const int i0 = 16 * mt + g, i1 = i0 + 8;
+    const int iy0 = i0 / WS, ix0 = i0 - iy0 * WS, iy1 = i1 / WS, ix1 = i1 - iy1 * WS;
+    const int reg0 = sm.reg[i0 & 63], reg1 = sm.reg[i1 & 63];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 8 * nt + 2 * q4 + e;
+        float s0 = -INFINITY, s1 = -INFINITY;
+        if (j < WT) {
+          const int jy = j / WS, jx = j - jy * WS;
+          const int regj = sm.reg[j];
+          if (i0 < WT) s0 = acc[nt][e] * scale + sm.tab[(iy0 - jy + WS - 1) * (2 * WS - 1) + (ix0 - jx + WS - 1)] + ((shift > 0 && regj != reg0) ? -100.f : 0.f);
+          if (i1 < WT) s1 = acc[nt][2 + e] * scale + sm.tab[(iy1 - jy + WS - 1) * (2 * WS - 1) + (ix1 - jx + WS - 1)] + ((shift > 0 && regj != reg1) ? -100.f : 0.f);
+        }
+        acc[nt][e] = s0; acc[nt][2 + e] = s1;
+        m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1);
+      }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    if (m0 == -INFINITY) m0 = 0.f;                                  // padded query rows
+    if (m1 == -INFINITY) m1 = 0.f;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float p0 = __expf(acc[nt][e] - m0), p1 = __expf(acc[nt][2 + e] - m1);
+        acc[nt][e] = p0; acc[nt][2 + e] = p1;
+        l0 += p0; l1 += p1;
+      }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // O = P V
+    float o[4][4];
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      uint32_t a[4];
+      a[0] = Mma16<T>::pack(acc[2 * kt][0], acc[2 * kt][1]);
+      a[1] = Mma16<T>::pack(acc[2 * kt][2], acc[2 * kt][3]);
+      a[2] = Mma16<T>::pack(acc[2 * kt + 1][0], acc[2 * kt + 1][1]);
+      a[3] = Mma16<T>::pack(acc[2 * kt + 1][2], acc[2 * kt + 1][3]);
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sm.vt[8 * dt + g][16 * kt + 2 * q4]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sm.vt[8 * dt + g][16 * kt + 8 + 2 * q4]);
+        Mma16<T>::mma(o[dt], a, b0, b1);
+      }
+    }
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    const int r0 = i0 < WT ? sm.row[i0] : -1, r1 = i1 < WT ? sm.row[i1] : -1;
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) {
+      if (r0 >= 0) *reinterpret_cast<uint32_t*>(out + (size_t)r0 * C + head * HD + 8 * dt + 2 * q4) = Mma16<T>::pack(o[dt][0] * inv0, o[dt][1] * inv0);
+      if (r1 >= 0) *reinterpret_cast<uint32_t*>(out + (size_t)r1 * C + head * HD + 8 * dt + 2 * q4) = Mma16<T>::pack(o[dt][2] * inv1, o[dt][3] * inv1);
+    }
+  }
+}
+
 int launch_window_attention(const void* qkv, const float* qkv_bias, const float* table, void* out, int dt, int B, int H, int C, int nH,
                             int shift, cudaStream_t s) {
   YB_REQUIRE(C == nH * HD, YB_ERR_UNSUPPORTED, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, nH);
   const int nW = (H + WS - 1) / WS;
+  if (dt != DT_F32 && !getenv("YOLACT_B200_NO_TC_ATTN")) {
+    const long long units = (long long)B * nW * nW * nH;
+    const int blocks = (int)((units + TCA_WARPS - 1) / TCA_WARPS);
+    if (dt == DT_F16) {
+      const size_t smem = sizeof(AttnSmem<__half>) * TCA_WARPS;
+      YB_CHECK_CUDA(cudaFuncSetAttribute(k_window_attention_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_window_attention_tc<__half><<<blocks, TCA_WARPS * 32, smem, s>>>((const __half*)qkv, qkv_bias, table, (__half*)out, B, H, C, nH, shift);
+    } else {
+      const size_t smem = sizeof(AttnSmem<__nv_bfloat16>) * TCA_WARPS;
+      YB_CHECK_CUDA(cudaFuncSetAttribute(k_window_attention_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_window_attention_tc<__nv_bfloat16><<<blocks, TCA_WARPS * 32, smem, s>>>((const __nv_bfloat16*)qkv, qkv_bias, table, (__nv_bfloat16*)out, B, H, C, nH, shift);
+    }
+    YB_CHECK_LAUNCH();
+    return YB_OK;
+  }
   dim3 grid(nW * nW, nH, B);
   YB_DISPATCH_DT(dt, (k_window_attention<T><<<grid, 64, 0, s>>>((const T*)qkv, qkv_bias, table, (T*)out, H, C, nH, shift)));
   YB_CHECK_LAUNCH();
