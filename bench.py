@@ -318,7 +318,8 @@ def run_ours(args):
                  'parity_vs_fp32_oracle_max_abs_err': {n: float(np.abs(m - r).max()) for n, m, r in zip(('cls', 'box', 'coef', 'proto'), m2, ref)}}
         eng = net2.engine(BATCH)
 
-    # ---- roofline of the dominant kernel ----    tc = prof['conv_tc'] if prof['conv_tc']['launches'] else prof['conv_simt']
+    # ---- roofline of the dominant kernel ----
+    tc = prof['conv_tc'] if prof['conv_tc']['launches'] else prof['conv_simt']
     dom = 'k_conv_tc' if prof['conv_tc']['launches'] else 'k_conv_simt'
     achieved = tc['flops'] / (tc['ms'] * 1e-3) / 1e12 if tc['ms'] else 0.0
     total_ms = sum(v['ms'] for v in prof.values())
