@@ -108,7 +108,7 @@ def forward(img, sd, arch='res101', num_classes=81, return_intermediates=False):
 
 
 # ----------------------------------------------------------------------------- synthetic weights
-def synth_state_dict(arch='res101', num_classes=81, num_ratios=3, seed=0, coef_dim=32):
+def synth_state_dict(arch='res101', num_classes=81, num_ratios=3, seed=0, coef_dim=32, train=False):
     """Deterministic random weights with the reference's state-dict layout:
     xavier-uniform-like conv weights (modules/yolact.py:120-125), non-trivial BN statistics
     (so BN folding is actually exercised), small non-zero biases."""
@@ -166,6 +166,8 @@ def synth_state_dict(arch='res101', num_classes=81, num_ratios=3, seed=0, coef_d
     conv(pl + 'bbox_layer', num_ratios * 4, 256, 3, True, gain=0.6)
     conv(pl + 'conf_layer', num_ratios * num_classes, 256, 3, True, gain=2.5)
     conv(pl + 'coef_layer.0', num_ratios * coef_dim, 256, 3, True, gain=0.8)
+    if train:
+        conv('semantic_seg_conv', num_classes - 1, 256, 1, True)
     return sd
 
 

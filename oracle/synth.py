@@ -77,3 +77,20 @@ def proto(seed, P, coef_dim=32):
 def image_batch(seed, B, S):
     """Mean/std-normalised RGB images are ~N(0,1) (utils/augmentations.py:212-216)."""
     return normal(seed, 5, (B, 3, S, S)).astype(np.float32)
+
+
+def train_targets(seed, B, S, n=3, num_classes=80):
+    """Synthetic training targets: per image n boxes [x1,y1,x2,y2,label]
+    in [0,1] and filled-rectangle masks [n,S,S] (float32)."""
+    targets, masks = [], []
+    for b in range(B):
+        xy = uniform(seed, 30 + b, (n, 2)) * 0.5
+        wh = uniform(seed, 60 + b, (n, 2)) * 0.4 + 0.1
+        lab = np.floor(uniform(seed, 90 + b, (n, 1)) * num_classes)
+        t = np.concatenate([xy, xy + wh, lab], 1).astype(np.float32)
+        m = np.zeros((n, S, S), np.float32)
+        for j in range(n):
+            x1, y1, x2, y2 = (t[j, :4] * S).astype(int)
+            m[j, y1:y2 + 1, x1:x2 + 1] = 1.0
+        targets.append(t); masks.append(m)
+    return targets, masks

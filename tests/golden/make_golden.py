@@ -267,16 +267,46 @@ def gen_val_aug():
     np.savez_compressed(os.path.join(HERE, 'val_aug.npz'), **out)
 
 
+def gen_train(rcfg, ryolact):
+    """Training-branch goldens: the reference's 4 losses, a few gradient norms and BN statistics after
+    one forward/backward on CPU (train mode, synthetic targets)."""
+    import contextlib, io, types
+    out = {}
+    for arch, S, B in (('res50', 128, 2), ('res101', 96, 2)):
+        ns = types.SimpleNamespace(cfg=arch + '_coco', img_size=S, weight=None, traditional_nms=False, resume=None, train_bs=B,
+                                   val_interval=-1, val_num=-1, coco_api=False)
+        with contextlib.redirect_stdout(io.StringIO()):
+            cfg = rcfg.get_config(ns, 'train')
+        sd = ft.synth_state_dict(arch, seed=0, train=True)
+        net = ryolact.Yolact(cfg)
+        net.load_state_dict(sd, strict=True)
+        net.train()
+        img = torch.from_numpy(synth.image_batch(11, B, S))
+        tg, mk = synth.train_targets(5, B, S)
+        losses = net(img, [torch.from_numpy(t) for t in tg], [torch.from_numpy(m) for m in mk])
+        sum(losses).backward()
+        key = f'{arch}_S{S}_B{B}'
+        out[key + '/losses'] = np.asarray([float(l) for l in losses], dtype=np.float64)
+        named = dict(net.named_parameters())
+        for pn in ('backbone.conv1.weight', 'backbone.layers.2.0.conv2.weight', 'fpn.lat_layers.0.bias', 'proto_net.proto2.2.weight',
+                   'prediction_layers.conf_layer.weight', 'semantic_seg_conv.weight'):
+            out[f'{key}/grad/{pn}'] = np.float64(named[pn].grad.double().norm())
+        out[key + '/bn1_mean'] = net.backbone.bn1.running_mean.detach().numpy().copy()
+        print(f'  train {key}: losses {[round(float(l), 5) for l in losses]}')
+    np.savez_compressed(os.path.join(HERE, 'train.npz'), **out)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     build_cython_nms()
     rcfg, ryolact, rout, rbox = import_reference()
-    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug']
+    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug', 'train']
     if 'anchors' in which: gen_anchors(rcfg, ryolact)
     if 'hard' in which: gen_hard_nms()
     if 'post' in which: gen_postprocess(rcfg, rout)
     if 'after' in which: gen_after_nms(rcfg, rout)
     if 'forward' in which: gen_forward(rcfg, ryolact)
     if 'valaug' in which: gen_val_aug()
+    if 'train' in which: gen_train(rcfg, ryolact)
     print('done')
