@@ -294,40 +294,37 @@ int launch_stem(const float* img, const float* w, const float* bias, void* out, 
 // ------------------------------------------------------------------------------------------------
 // max-pool 3x3 s2 p1 on post-ReLU data (zero halo == -inf padding because everything is >= 0)
 // ------------------------------------------------------------------------------------------------
+// Elementwise kernels use a (x*channel-vectors, y, image) launch geometry: no 64-bit index arithmetic
+// (the first versions spent ~75 % of their issue slots on long-long div/mod).
 template <typename T>
-__global__ void k_maxpool(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout) {
+__global__ void __launch_bounds__(256) k_maxpool(const T* __restrict__ in, T* __restrict__ out, int C, int Hin, int Hout) {
   constexpr int N = VecIO<T>::N;
   const int Hpi = Hin + 2, Hpo = Hout + 2, CV = C / N;
-  const long long total = (long long)B * Hpo * Hpo * CV;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    long long r = i / CV;
-    const int xp = (int)(r % Hpo); r /= Hpo;
-    const int yp = (int)(r % Hpo);
-    const int b = (int)(r / Hpo);
-    float m[N];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Hpo * CV) return;
+  const int xp = t / CV, cv = t - xp * CV, yp = blockIdx.y, b = blockIdx.z;
+  float m[N];
 #pragma unroll
-    for (int q = 0; q < N; ++q) m[q] = 0.f;
-    if (yp >= 1 && yp <= Hout && xp >= 1 && xp <= Hout) {
-      const int y = yp - 1, x = xp - 1;                      // window rows 2y-1..2y+1 -> haloed 2y..2y+2
+  for (int q = 0; q < N; ++q) m[q] = 0.f;
+  if (yp >= 1 && yp <= Hout && xp >= 1 && xp <= Hout) {
+    const int y = yp - 1, x = xp - 1;                      // window rows 2y-1..2y+1 -> haloed 2y..2y+2
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          float v[N];
-          VecIO<T>::load(in + (((size_t)b * Hpi + 2 * y + dy) * Hpi + 2 * x + dx) * C + cv * N, v);
+      for (int dx = 0; dx < 3; ++dx) {
+        float v[N];
+        VecIO<T>::load(in + (((size_t)b * Hpi + 2 * y + dy) * Hpi + 2 * x + dx) * C + cv * N, v);
 #pragma unroll
-          for (int q = 0; q < N; ++q) m[q] = fmaxf(m[q], v[q]);
-        }
-    }
-    VecIO<T>::store(out + i * N, m);
+        for (int q = 0; q < N; ++q) m[q] = fmaxf(m[q], v[q]);
+      }
   }
+  VecIO<T>::store(out + (((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N, m);
 }
 
 int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s) {
-  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C / 4;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  YB_DISPATCH_DT(dt, (k_maxpool<T><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout)));
+  const int cv = C / (dt == DT_F32 ? 4 : 8);
+  dim3 grid(ceil_div((Hout + 2) * cv, 256), Hout + 2, B);
+  YB_DISPATCH_DT(dt, (k_maxpool<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, C, Hin, Hout)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -337,34 +334,28 @@ int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int
 // [-1, Hout], stored with the OUTPUT's haloed geometry.  nplanes = 4 (3x3 s2) or 1 (1x1 s2).
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_phase_split(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout,
-                              int nplanes, long long plane_stride_rows) {
+__global__ void __launch_bounds__(256) k_phase_split(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout,
+                                                     long long plane_stride_rows) {
   constexpr int N = VecIO<T>::N;
   const int Hpi = Hin + 2, Hpo = Hout + 2, CV = C / N;
-  const long long per_plane = (long long)B * Hpo * Hpo * CV;
-  const long long total = per_plane * nplanes;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int pl = (int)(i / per_plane);
-    long long r = i - pl * per_plane;
-    const int cv = (int)(r % CV); r /= CV;
-    const int xp = (int)(r % Hpo); r /= Hpo;
-    const int yp = (int)(r % Hpo);
-    const int b = (int)(r / Hpo);
-    const int p = pl >> 1, q = pl & 1;
-    const int iy = 2 * (yp - 1) + p, ix = 2 * (xp - 1) + q;
-    float v[N];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Hpo * CV) return;
+  const int xp = t / CV, cv = t - xp * CV, yp = blockIdx.y;
+  const int pl = blockIdx.z / B, b = blockIdx.z - pl * B;
+  const int p = pl >> 1, q = pl & 1;
+  const int iy = 2 * (yp - 1) + p, ix = 2 * (xp - 1) + q;
+  float v[N];
 #pragma unroll
-    for (int e = 0; e < N; ++e) v[e] = 0.f;
-    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) VecIO<T>::load(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + cv * N, v);
-    VecIO<T>::store(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N, v);
-  }
+  for (int e = 0; e < N; ++e) v[e] = 0.f;
+  if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) VecIO<T>::load(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + cv * N, v);
+  VecIO<T>::store(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N, v);
 }
 
 int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
                        long long plane_stride_rows, cudaStream_t s) {
-  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C * nplanes / 4;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  YB_DISPATCH_DT(dt, (k_phase_split<T><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, nplanes, plane_stride_rows)));
+  const int cv = C / (dt == DT_F32 ? 4 : 8);
+  dim3 grid(ceil_div((Hout + 2) * cv, 256), Hout + 2, B * nplanes);
+  YB_DISPATCH_DT(dt, (k_phase_split<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, plane_stride_rows)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -381,50 +372,46 @@ __device__ __forceinline__ void src_index(int dst, float scale, bool align, int 
 }
 
 template <typename T, bool kAdd, bool kAlign>
-__global__ void k_bilinear(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int Hs, int Hd, float scale) {
+__global__ void __launch_bounds__(256) k_bilinear(const T* __restrict__ src, T* __restrict__ dst, int C, int Hs, int Hd, float scale) {
   constexpr int N = VecIO<T>::N;
   const int Hps = Hs + 2, Hpd = Hd + 2, CV = C / N;
-  const long long total = (long long)B * Hpd * Hpd * CV;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    long long r = i / CV;
-    const int xp = (int)(r % Hpd); r /= Hpd;
-    const int yp = (int)(r % Hpd);
-    const int b = (int)(r / Hpd);
-    const bool halo = yp == 0 || yp == Hd + 1 || xp == 0 || xp == Hd + 1;
-    float v[N];
-    if (halo) {
-      if (!kAdd) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Hpd * CV) return;
+  const int xp = t / CV, cv = t - xp * CV, yp = blockIdx.y, b = blockIdx.z;
+  T* d = dst + (((size_t)b * Hpd + yp) * Hpd + xp) * C + cv * N;
+  const bool halo = yp == 0 || yp == Hd + 1 || xp == 0 || xp == Hd + 1;
+  float v[N];
+  if (halo) {
+    if (!kAdd) {
 #pragma unroll
-        for (int e = 0; e < N; ++e) v[e] = 0.f;
-        VecIO<T>::store(dst + i * N, v);
-      }
-      continue;
+      for (int e = 0; e < N; ++e) v[e] = 0.f;
+      VecIO<T>::store(d, v);
     }
-    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
-    src_index(yp - 1, scale, kAlign, Hs, y0, y1, ly0, ly1);
-    src_index(xp - 1, scale, kAlign, Hs, x0, x1, lx0, lx1);
-    const T* sb = src + (size_t)b * Hps * Hps * C + cv * N;
-    float v00[N], v01[N], v10[N], v11[N];
-    VecIO<T>::load(sb + ((size_t)(y0 + 1) * Hps + x0 + 1) * C, v00);
-    VecIO<T>::load(sb + ((size_t)(y0 + 1) * Hps + x1 + 1) * C, v01);
-    VecIO<T>::load(sb + ((size_t)(y1 + 1) * Hps + x0 + 1) * C, v10);
-    VecIO<T>::load(sb + ((size_t)(y1 + 1) * Hps + x1 + 1) * C, v11);
-    if (kAdd) VecIO<T>::load(dst + i * N, v);
-#pragma unroll
-    for (int e = 0; e < N; ++e) {
-      const float t = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
-      v[e] = kAdd ? v[e] + t : t;
-    }
-    VecIO<T>::store(dst + i * N, v);
+    return;
   }
+  int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+  src_index(yp - 1, scale, kAlign, Hs, y0, y1, ly0, ly1);
+  src_index(xp - 1, scale, kAlign, Hs, x0, x1, lx0, lx1);
+  const T* sb = src + (size_t)b * Hps * Hps * C + cv * N;
+  float v00[N], v01[N], v10[N], v11[N];
+  VecIO<T>::load(sb + ((size_t)(y0 + 1) * Hps + x0 + 1) * C, v00);
+  VecIO<T>::load(sb + ((size_t)(y0 + 1) * Hps + x1 + 1) * C, v01);
+  VecIO<T>::load(sb + ((size_t)(y1 + 1) * Hps + x0 + 1) * C, v10);
+  VecIO<T>::load(sb + ((size_t)(y1 + 1) * Hps + x1 + 1) * C, v11);
+  if (kAdd) VecIO<T>::load(d, v);
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+    const float tt = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
+    v[e] = kAdd ? v[e] + tt : tt;
+  }
+  VecIO<T>::store(d, v);
 }
 
 int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, int Hc, int Hf, cudaStream_t s) {
-  const long long total = (long long)B * (Hf + 2) * (Hf + 2) * C / 4;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const int cv = C / (dt == DT_F32 ? 4 : 8);
+  dim3 grid(ceil_div((Hf + 2) * cv, 256), Hf + 2, B);
   const float scale = (float)Hc / (float)Hf;
-  YB_DISPATCH_DT(dt, (k_bilinear<T, true, false><<<blocks, 256, 0, s>>>((const T*)coarse, (T*)fine, B, C, Hc, Hf, scale)));
+  YB_DISPATCH_DT(dt, (k_bilinear<T, true, false><<<grid, 256, 0, s>>>((const T*)coarse, (T*)fine, C, Hc, Hf, scale)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -432,10 +419,10 @@ int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, in
 // protonet: bilinear x2, align_corners=True (modules/yolact.py:43,:51)
 int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hin, cudaStream_t s) {
   const int Hout = 2 * Hin;
-  const long long total = (long long)B * (Hout + 2) * (Hout + 2) * C / 4;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const int cv = C / (dt == DT_F32 ? 4 : 8);
+  dim3 grid(ceil_div((Hout + 2) * cv, 256), Hout + 2, B);
   const float scale = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
-  YB_DISPATCH_DT(dt, (k_bilinear<T, false, true><<<blocks, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, scale)));
+  YB_DISPATCH_DT(dt, (k_bilinear<T, false, true><<<grid, 256, 0, s>>>((const T*)in, (T*)out, C, Hin, Hout, scale)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -446,41 +433,45 @@ int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hi
 // [B, A, C] / [B, A, 4] / [B, A, K] layout (modules/yolact.py:26-31,:155-163).
 // head row layout: [conf: R*C | box: R*4 | coef: R*K | pad]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_head_finalize(const float* __restrict__ head, int ld, int B, int HW, int R, int NC, int K,
+__global__ void __launch_bounds__(256) k_head_finalize(const float* __restrict__ head, int ld, int HW, int R, int NC, int K,
                                                        int anchor_offset, int A_total, float* __restrict__ cls,
                                                        float* __restrict__ box, float* __restrict__ coef) {
   const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long total = (long long)B * HW * R;
-  for (long long wi = warp; wi < total; wi += nwarps) {
-    const int a = (int)(wi % R);
-    const long long pr = wi / R;                  // b*HW + pix
-    const int b = (int)(pr / HW), pix = (int)(pr - (long long)b * HW);
-    const float* row = head + pr * ld;
-    const long long arow = (long long)b * A_total + anchor_offset + (long long)pix * R + a;
-    // softmax over NC logits
-    const float* lg = row + a * NC;
-    float mx = -INFINITY;
-    for (int c = lane; c < NC; c += 32) mx = fmaxf(mx, lg[c]);
+  const int wi = blockIdx.x * 8 + (threadIdx.x >> 5);              // (pixel, anchor) within the image
+  if (wi >= HW * R) return;
+  const int b = blockIdx.y;
+  const int pix = wi / R, a = wi - pix * R;
+  const float* row = head + ((size_t)b * HW + pix) * ld;
+  const size_t arow = (size_t)b * A_total + anchor_offset + (size_t)pix * R + a;
+  const float* lg = row + a * NC;
+  float mx = -INFINITY;
+  for (int c = lane; c < NC; c += 32) mx = fmaxf(mx, lg[c]);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    float sum = 0.f;
-    for (int c = lane; c < NC; c += 32) sum += expf(lg[c] - mx);
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float ex[4] = {0.f, 0.f, 0.f, 0.f};                              // NC <= 128
+  float sum = 0.f;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    const float inv = 1.f / sum;
-    for (int c = lane; c < NC; c += 32) cls[arow * NC + c] = expf(lg[c] - mx) * inv;
-    if (lane < 4) box[arow * 4 + lane] = row[R * NC + a * 4 + lane];
-    for (int k = lane; k < K; k += 32) coef[arow * K + k] = tanhf(row[R * NC + R * 4 + a * K + k]);
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i;
+    if (c < NC) { ex[i] = __expf(lg[c] - mx); sum += ex[i]; }
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i;
+    if (c < NC) cls[arow * NC + c] = ex[i] * inv;
+  }
+  if (lane < 4) box[arow * 4 + lane] = row[R * NC + a * 4 + lane];
+  for (int k = lane; k < K; k += 32) coef[arow * K + k] = tanhf(row[R * NC + R * 4 + a * K + k]);
 }
 
 int launch_head_finalize(const float* head, int ld, int B, int HW, int R, int NC, int K, int anchor_offset, int A_total,
                          float* cls, float* box, float* coef, cudaStream_t s) {
-  const long long total = (long long)B * HW * R;
-  const int blocks = (int)std::min<long long>((total * 32 + 255) / 256, 148LL * 16);
-  k_head_finalize<<<blocks, 256, 0, s>>>(head, ld, B, HW, R, NC, K, anchor_offset, A_total, cls, box, coef);
+  YB_REQUIRE(NC <= 128, YB_ERR_UNSUPPORTED, "head_finalize: num_classes=%d > 128", NC);
+  dim3 grid(ceil_div(HW * R, 8), B);
+  k_head_finalize<<<grid, 256, 0, s>>>(head, ld, HW, R, NC, K, anchor_offset, A_total, cls, box, coef);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }

@@ -38,9 +38,10 @@ __global__ void __launch_bounds__(256) k_patch_embed(const float* __restrict__ i
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int Hp = Hg + 2;
-  const long long total = (long long)B * Hp * Hp;
-  for (long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tok < total; tok += (long long)gridDim.x * 8) {
-    const int xp = (int)(tok % Hp), yp = (int)((tok / Hp) % Hp), b = (int)(tok / ((long long)Hp * Hp));
+  const int b = blockIdx.y;                                        // 32-bit index math only
+  for (int ti = blockIdx.x * 8 + (threadIdx.x >> 5); ti < Hp * Hp; ti += gridDim.x * 8) {
+    const int yp = ti / Hp, xp = ti - yp * Hp;
+    const size_t tok = (size_t)b * Hp * Hp + ti;
     T* o = out + tok * 96;
     if (yp == 0 || yp == Hg + 1 || xp == 0 || xp == Hg + 1) {
       for (int c = lane; c < 96; c += 32) tok_st<T>(o + c, 0.f);
@@ -76,9 +77,8 @@ __global__ void __launch_bounds__(256) k_patch_embed(const float* __restrict__ i
 
 int launch_patch_embed(const float* img, const float* w, const float* bias, const float* g, const float* be, void* out, int dt,
                        int B, int S, int Hg, cudaStream_t s) {
-  const long long total = (long long)B * (Hg + 2) * (Hg + 2);
-  const int blocks = (int)std::min<long long>((total + 7) / 8, 148LL * 16);
-  YB_DISPATCH_DT(dt, (k_patch_embed<T><<<blocks, 256, 0, s>>>(img, w, bias, g, be, (T*)out, B, S, Hg)));
+  dim3 grid(std::min(((Hg + 2) * (Hg + 2) + 7) / 8, 148 * 4), B);
+  YB_DISPATCH_DT(dt, (k_patch_embed<T><<<grid, 256, 0, s>>>(img, w, bias, g, be, (T*)out, B, S, Hg)));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -130,12 +130,12 @@ __global__ void __launch_bounds__(256) k_layernorm(const T* __restrict__ in, T* 
   constexpr int N = TokVec<T>::N, TPW = 32 / G;
   const int lane = threadIdx.x & 31, sub = lane % G;
   const int Hp = H + 2, nvec = C / N;
-  const long long total = (long long)B * Hp * Hp;
-  const long long stride = (long long)gridDim.x * 8 * TPW;
-  for (long long tok0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * TPW; tok0 < total; tok0 += stride) {
-    const long long tok = tok0 + lane / G;
-    const bool live = tok < total;
-    const int xp = (int)(tok % Hp), yp = (int)((tok / Hp) % Hp);
+  const int per_img = Hp * Hp, b = blockIdx.y;
+  for (int t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * TPW; t0 < per_img; t0 += gridDim.x * 8 * TPW) {
+    const int ti = t0 + lane / G;
+    const bool live = ti < per_img;
+    const int yp = ti / Hp, xp = ti - yp * Hp;
+    const size_t tok = (size_t)b * per_img + ti;
     const T* x = in + tok * C;
     T* o = out + tok * C;
     const bool halo = yp == 0 || yp == H + 1 || xp == 0 || xp == H + 1;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_layernorm(const T* __restrict__ in, T* 
 }
 
 template <typename T>
-static void layernorm_dispatch(const T* in, T* out, const float* g, const float* be, int B, int C, int H, int nvec, int blocks, cudaStream_t s) {
+static void layernorm_dispatch(const T* in, T* out, const float* g, const float* be, int B, int C, int H, int nvec, dim3 blocks, cudaStream_t s) {
   if (nvec <= 16) k_layernorm<T, 1, 16><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, H);
   else if (nvec <= 32) k_layernorm<T, 1, 32><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, H);
   else if (nvec <= 64) k_layernorm<T, 2, 32><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, H);
@@ -191,8 +191,7 @@ static void layernorm_dispatch(const T* in, T* out, const float* g, const float*
 int launch_layernorm(const void* in, void* out, const float* g, const float* be, int dt, int B, int C, int H, cudaStream_t s) {
   const int nvec = C / (dt == DT_F32 ? 4 : 8);
   YB_REQUIRE(C % (dt == DT_F32 ? 4 : 8) == 0 && nvec <= 192, YB_ERR_UNSUPPORTED, "layernorm: C=%d", C);
-  const long long total = (long long)B * (H + 2) * (H + 2);
-  const int blocks = (int)std::min<long long>((total + 7) / 8, 148LL * 16);
+  const dim3 blocks(std::min(((H + 2) * (H + 2) + 7) / 8, 148 * 4), B);
   YB_DISPATCH_DT(dt, (layernorm_dispatch<T>((const T*)in, (T*)out, g, be, B, C, H, nvec, blocks, s)));
   YB_CHECK_LAUNCH();
   return YB_OK;
@@ -208,9 +207,10 @@ __global__ void __launch_bounds__(256) k_patch_merge_ln(const T* __restrict__ in
   constexpr int N = TokVec<T>::N;
   const int lane = threadIdx.x & 31;
   const int Hpi = Hin + 2, Hpo = Hout + 2, C4 = 4 * C, nvec = C4 / N, vpp = C / N;     // vectors per source token
-  const long long total = (long long)B * Hpo * Hpo;
-  for (long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tok < total; tok += (long long)gridDim.x * 8) {
-    const int xp = (int)(tok % Hpo), yp = (int)((tok / Hpo) % Hpo), b = (int)(tok / ((long long)Hpo * Hpo));
+  const int b = blockIdx.y;
+  for (int ti = blockIdx.x * 8 + (threadIdx.x >> 5); ti < Hpo * Hpo; ti += gridDim.x * 8) {
+    const int yp = ti / Hpo, xp = ti - yp * Hpo;
+    const size_t tok = (size_t)b * Hpo * Hpo + ti;
     T* o = out + tok * C4;
     const bool halo = yp == 0 || yp == Hout + 1 || xp == 0 || xp == Hout + 1;
     const int y = yp - 1, x = xp - 1;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_patch_merge_ln(const T* __restrict__ in
 }
 
 template <typename T>
-static void patch_merge_dispatch(const T* in, T* out, const float* g, const float* be, int B, int C, int Hin, int Hout, int nvec, int blocks,
+static void patch_merge_dispatch(const T* in, T* out, const float* g, const float* be, int B, int C, int Hin, int Hout, int nvec, dim3 blocks,
                                  cudaStream_t s) {
   if (nvec <= 64) k_patch_merge_ln<T, 2><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, Hin, Hout);
   else if (nvec <= 96) k_patch_merge_ln<T, 3><<<blocks, 256, 0, s>>>(in, out, g, be, B, C, Hin, Hout);
@@ -267,8 +267,7 @@ int launch_patch_merge_ln(const void* in, void* out, const float* g, const float
                           cudaStream_t s) {
   const int N = dt == DT_F32 ? 4 : 8, nvec = 4 * C / N;
   YB_REQUIRE(C % N == 0 && nvec <= 384, YB_ERR_UNSUPPORTED, "patch_merge_ln: C=%d", C);
-  const long long total = (long long)B * (Hout + 2) * (Hout + 2);
-  const int blocks = (int)std::min<long long>((total + 7) / 8, 148LL * 16);
+  const dim3 blocks(std::min(((Hout + 2) * (Hout + 2) + 7) / 8, 148 * 4), B);
   YB_DISPATCH_DT(dt, (patch_merge_dispatch<T>((const T*)in, (T*)out, g, be, B, C, Hin, Hout, nvec, blocks, s)));
   YB_CHECK_LAUNCH();
   return YB_OK;
