@@ -210,4 +210,12 @@ def make_config(name='res101_coco', img_size=544, mode='detect', **overrides):
                                coco_api=False, resume=None, train_bs=8, val_interval=-1, verbose=False)
     for k, v in overrides.items():
         setattr(ns, k, v)
-    return get_config(ns, mode)
+    # like get_config, minus the process-group initialisation and the printing
+    ns.cuda, ns.mode = torch.cuda.is_available(), mode
+    ns.gpu_id = (os.environ.get('CUDA_VISIBLE_DEVICES') or '0') if ns.cuda else None
+    if mode == 'train' and not hasattr(ns, 'bs_per_gpu'):
+        ns.bs_per_gpu = ns.train_bs
+    cls = globals().get(name)
+    if not (isinstance(cls, type) and issubclass(cls, _BaseConfig)):
+        raise KeyError(f'unknown config {name!r}')
+    return cls(ns)
