@@ -489,11 +489,11 @@ static EncodeTiledFn get_encode() {
 }
 
 static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows, bool f16,
-                    uint32_t box_inner = TC_BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    uint32_t box_inner = TC_BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t row_stride = 0) {
   EncodeTiledFn enc = get_encode();
   YB_REQUIRE(enc != nullptr, YB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[2] = {inner, rows};
-  const cuuint64_t strides[1] = {inner * 2};
+  const cuuint64_t strides[1] = {(row_stride ? row_stride : inner) * 2};
   const cuuint32_t box[2] = {box_inner, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -502,6 +502,22 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   YB_REQUIRE(r == CUDA_SUCCESS, YB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu box_rows=%u", (int)r,
              (unsigned long long)inner, (unsigned long long)rows, box_rows);
   return YB_OK;
+}
+
+bool tc_overlapping_rows_ok() {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  alignas(64) static CUtensorMap probe;
+  const cuuint64_t dims[2] = {64, 4096};
+  const cuuint64_t strides[1] = {32};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  void* base = nullptr;
+  if (cudaMalloc(&base, 4096 * 32 + 128) != cudaSuccess) { cudaGetLastError(); return false; }
+  const CUresult r = enc(&probe, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cudaFree(base);
+  return r == CUDA_SUCCESS;
 }
 
 static int pick_bn(int cout_pad) {
@@ -553,7 +569,7 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   const int Ktot = a.ntaps * a.Cin_pad;
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
-  int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, TC_BM, f16);
+  int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.in_row_stride);
   if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)pl->BN, f16);
   pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;                      // placeholders when the TMA epilogue is off
   if (s == YB_OK && pl->tma_epi) {

@@ -258,6 +258,61 @@ int launch_stem_im2col(const float* img, void* cols, int dt, int B, int S, int H
   return YB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// stem, 16-bit modes: space-to-depth repack.  The 7x7 stride-2 convolution over 3 channels equals a 4x4
+// stride-1 convolution over the 12 channels (py, px, ci) of the 2x2 space-to-depth image (one all-zero tap
+// row/column pads 7 to 8).  This kernel writes that image, 16-bit, channels padded 12 -> 16, on the SAME
+// haloed pixel grid as the stem output:  s2d[b][Y][X][(py*2+px)*3+ci] = img[b][ci][2Y+py-4][2X+px-4]
+// (zero outside the image), so tap (dy, dx) of output pixel m is pixel m + (dy-1)*Wp - 1 + dx.  The four dx
+// taps of one dy are 64 CONTIGUOUS elements starting at that pixel: with WIDE=false the tensor-core kernel
+// reads them through a tensor map whose rows overlap (row stride 16 elements, row length 64); WIDE=true
+// materialises the four pixels per row ([pixel][64]) for drivers that refuse an overlapping map.
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool WIDE>
+__global__ void __launch_bounds__(160) k_stem_s2d(const float* __restrict__ img, T* __restrict__ out, int S, int Hp) {
+  const int X = blockIdx.x * 160 + threadIdx.x, Y = blockIdx.y, b = blockIdx.z;
+  if (X >= Hp) return;
+  constexpr int NP = WIDE ? 4 : 1;
+  T* dst = out + (((size_t)b * Hp + Y) * Hp + X) * (16 * NP);
+#pragma unroll
+  for (int d = 0; d < NP; ++d) {
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    const int ix0 = 2 * (X + d) - 4;
+    if (X + d < Hp) {
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const int iy = 2 * Y + py - 4;
+        if (iy < 0 || iy >= S) continue;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float* row = img + (((size_t)b * 3 + ci) * S + iy) * S;
+          if (ix0 >= 0 && ix0 < S) v[(py * 2 + 0) * 3 + ci] = __ldg(row + ix0);
+          if (ix0 + 1 >= 0 && ix0 + 1 < S) v[(py * 2 + 1) * 3 + ci] = __ldg(row + ix0 + 1);
+        }
+      }
+    }
+    VecIO<T>::store(dst + d * 16, v);
+    VecIO<T>::store(dst + d * 16 + 8, v + 8);
+  }
+}
+
+int launch_stem_s2d(const float* img, void* out, int dt, int wide, int B, int S, int H1, cudaStream_t s) {
+  YB_REQUIRE(dt != DT_F32, YB_ERR_INVALID, "stem_s2d is for the 16-bit modes");
+  const int Hp = H1 + 2;
+  dim3 grid(ceil_div(Hp, 160), Hp, B);
+  if (dt == DT_BF16) {
+    if (wide) k_stem_s2d<__nv_bfloat16, true><<<grid, 160, 0, s>>>(img, (__nv_bfloat16*)out, S, Hp);
+    else k_stem_s2d<__nv_bfloat16, false><<<grid, 160, 0, s>>>(img, (__nv_bfloat16*)out, S, Hp);
+  } else {
+    if (wide) k_stem_s2d<__half, true><<<grid, 160, 0, s>>>(img, (__half*)out, S, Hp);
+    else k_stem_s2d<__half, false><<<grid, 160, 0, s>>>(img, (__half*)out, S, Hp);
+  }
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
 template <typename T>
 __global__ void k_zero_halo(T* __restrict__ t, int B, int C, int H) {
   // zero the 1-pixel frame of a haloed tensor [B][H+2][H+2][C]

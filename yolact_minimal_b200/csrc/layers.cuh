@@ -43,6 +43,7 @@ struct ConvArgs {
   int relu;              // activation: 0 none, 1 ReLU, 2 exact (erf) GELU
   int out_mode;          // 0: haloed NHWC act_dt, halo zeroed;  1: dense fp32 [B*H*W][Cout] (halo rows skipped)
   long long in_rows;     // total rows addressable in `in` (for bounds checks)
+  int in_row_stride;     // tensor-core path: elements between consecutive rows of `in` (0 = Cin; < Cin = overlapping rows, stem)
 };
 
 // run `expr` with type alias T bound to the C++ type of DType dt
@@ -65,6 +66,8 @@ bool tc_supported(const ConvArgs& a);
 
 int launch_stem(const float* img_nchw, const float* w /*[7][7][3][64]*/, const float* bias, void* out, int out_dt,
                 int B, int S, int H1, cudaStream_t s);
+int launch_stem_s2d(const float* img_nchw, void* out /*[B][(H1+2)^2][16 | 64]*/, int dt, int wide, int B, int S, int H1, cudaStream_t s);
+bool tc_overlapping_rows_ok();   // can the driver encode a tensor map whose rows overlap (row stride < row length)?
 int launch_stem_im2col(const float* img_nchw, void* cols /*[B*(H1+2)^2][192]*/, int dt, int B, int S, int H1, cudaStream_t s);
 int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s);
 int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,

@@ -80,7 +80,8 @@ struct yb_net {
   float* d_stem_b = nullptr;
   std::map<std::string, float*> d_vec;      // Swin: LayerNorm / attention parameters on the device (fp32)
   float* d_pe_w = nullptr;                  // Swin patch embedding weights [48][96]
-  void* d_stem_w16 = nullptr;               // 16-bit modes: [64][192] GEMM weights (k = (r*7+s)*3+ci)
+  void* d_stem_w16 = nullptr;               // 16-bit modes: [64][256] GEMM weights (k = dy*64 + dx*16 + (py*2+px)*3+ci)
+  int stem_wide = 0;                        // s2d rows materialised 4 pixels wide (driver refused overlapping tensor-map rows)
   float* d_stem_b16 = nullptr;
   ConvArgs stem_args{};
   // scratch for yb_net_detect_host
@@ -216,7 +217,11 @@ void build_program(yb_net* net) {
   net->add_param("backbone.conv1.weight", 64 * 3 * 7 * 7);
   for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) net->add_param(std::string("backbone.bn1") + s, 64);
   const int stem = new_act(net, 64, net->H1);
-  const int stem_cols = new_act(net, 152, net->H1);          // im2col rows: K = 147 padded to 152 (kernels_simt.cu kStemK)
+  // 16-bit modes: space-to-depth repack of the image (kernels_simt.cu k_stem_s2d), 16 channels per pixel; the
+  // tcgen05 kernel then runs the stem as a 4-tap K=64 convolution over it.  YOLACT_B200_STEM_WIDE=1 forces the
+  // 64-channel materialised form that is otherwise only the fallback when the overlapping tensor map is refused.
+  net->stem_wide = (getenv("YOLACT_B200_STEM_WIDE") || !tc_overlapping_rows_ok()) ? 1 : 0;
+  const int stem_cols = new_act(net, net->stem_wide ? 64 : 16, net->H1);
   { Op o; o.kind = OP_STEM; o.out = stem; o.aux = stem_cols; net->ops.push_back(o); }
   int x = new_act(net, 64, net->H2);
   { Op o; o.kind = OP_POOL; o.in = stem; o.out = x; net->ops.push_back(o); }
@@ -580,13 +585,20 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   YB_PROPAGATE(upload(net->anchors.data(), net->anchors.size() * 4, (void**)&net->d_anchors));
   // tensor-core plans (16-bit operand modes)
   if (net->act_dt != DT_F32 && !getenv("YOLACT_B200_NO_TC")) {
-    if (net->cfg.depth != 0) {  // stem as a GEMM over im2col rows: [B*(H1+2)^2][192] x [192][64]
-      std::vector<float> sc, sh, w((size_t)64 * 192, 0.f);
+    if (net->cfg.depth != 0) {  // stem as a 4-tap (dy) K=64 (dx x 16 ch) GEMM over the space-to-depth image
+      std::vector<float> sc, sh, w((size_t)64 * 256, 0.f);
       bn_fold(net, "backbone.bn1", 64, sc, sh);
       const auto& src = net->P_("backbone.conv1.weight");
       for (int co = 0; co < 64; ++co)
-        for (int ci = 0; ci < 3; ++ci)
-          for (int t = 0; t < 49; ++t) w[(size_t)co * 192 + t * 3 + ci] = src[((size_t)co * 3 + ci) * 49 + t] * sc[co];
+        for (int dy = 0; dy < 4; ++dy)
+          for (int dx = 0; dx < 4; ++dx)
+            for (int py = 0; py < 2; ++py)
+              for (int px = 0; px < 2; ++px) {
+                const int r = 2 * dy + py - 1, q = 2 * dx + px - 1;      // 7x7 tap; -1 = the zero pad tap
+                if (r < 0 || q < 0) continue;
+                for (int ci = 0; ci < 3; ++ci)
+                  w[(size_t)co * 256 + dy * 64 + dx * 16 + (py * 2 + px) * 3 + ci] = src[((size_t)co * 3 + ci) * 49 + r * 7 + q] * sc[co];
+              }
       if (net->act_dt == DT_BF16) { std::vector<__nv_bfloat16> t(w.size()); for (size_t i = 0; i < w.size(); ++i) t[i] = __float2bfloat16_rn(w[i]); YB_PROPAGATE(upload(t.data(), t.size() * 2, &net->d_stem_w16)); }
       else { std::vector<__half> t(w.size()); for (size_t i = 0; i < w.size(); ++i) t[i] = __float2half_rn(w[i]); YB_PROPAGATE(upload(t.data(), t.size() * 2, &net->d_stem_w16)); }
       YB_PROPAGATE(upload(sh.data(), sh.size() * 4, (void**)&net->d_stem_b16));
@@ -594,9 +606,11 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
       ConvArgs& a = net->stem_args;
       memset(&a, 0, sizeof(a));
       a.in = act_ptr(net, so.aux); a.weight = net->d_stem_w16; a.bias = net->d_stem_b16; a.out = act_ptr(net, so.out);
-      a.act_dt = net->act_dt; a.B = max_batch; a.g.H = net->H1; a.g.W = net->H1; a.Cin = 152; a.Cin_pad = 192; a.Cout = 64; a.Cout_pad = 64;
-      a.ntaps = 1; a.tap_shift[0] = 0; a.relu = 1; a.out_mode = 0;
+      a.act_dt = net->act_dt; a.B = max_batch; a.g.H = net->H1; a.g.W = net->H1; a.Cin = 64; a.Cin_pad = 64; a.Cout = 64; a.Cout_pad = 64;
+      a.ntaps = 4; a.relu = 1; a.out_mode = 0;
+      for (int dy = 0; dy < 4; ++dy) a.tap_shift[dy] = (dy - 1) * (net->H1 + 2) - 1;
       a.in_rows = (long long)max_batch * (net->H1 + 2) * (net->H1 + 2);
+      if (!net->stem_wide) { a.in_row_stride = 16; a.in_rows -= 3; }   // rows overlap: row p = pixels p .. p+3
       YB_PROPAGATE(tc_plan_create(a, max_batch, &so.tc));
     }
     for (auto& o : net->ops) {
@@ -641,7 +655,7 @@ extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* c
     switch (o.kind) {
       case OP_STEM:
         if (o.tc) {
-          YB_PROPAGATE(launch_stem_im2col(img, act_ptr(net, o.aux), net->act_dt, batch, cfg.img_size, net->H1, s));
+          YB_PROPAGATE(launch_stem_s2d(img, act_ptr(net, o.aux), net->act_dt, net->stem_wide, batch, cfg.img_size, net->H1, s));
           ConvArgs a = net->stem_args;
           a.B = batch;
           YB_PROPAGATE(launch_conv_tc(o.tc, a, s));
