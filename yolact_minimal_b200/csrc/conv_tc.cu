@@ -45,6 +45,9 @@ struct TcParams {
   int tma_epi;            // out_mode 0 && BN % 32 == 0: smem-staged TMA stores (+ TMA-prefetched residual)
   int nres;               // residual prefetch buffers (0 if none)
   int b_resident;         // weights of the CTA's N tile stay in shared memory for all its M tiles
+  int res_kb;             // > 0: the residual is added BY THE TENSOR CORE: BN/64 extra k-blocks whose A tile is the
+                          // residual's [128 x 64] slab and whose B tile is a shared-memory 64x64 identity (N=64 MMAs
+                          // into the matching 64 accumulator columns) -- the epilogue never touches the residual
   Geom g;
   const float* bias;
   const void* residual;
@@ -53,7 +56,7 @@ struct TcParams {
 
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult;
+  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb;
   size_t smem_bytes;
 };
 
@@ -94,6 +97,10 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+// programmatic dependent launch: let the next grid's CTAs take over SMs as ours retire / block until the previous grid's
+// memory is complete and visible (both are no-ops for a launch without the programmatic-serialization attribute)
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -153,6 +160,18 @@ template <bool F16> __device__ __forceinline__ uint32_t pack2_raw(float a, float
   if (F16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// one F2FP per pair: round-to-nearest pack with the fp16 range clamp (and optionally ReLU) folded into the conversion
+template <bool F16, bool RELU> __device__ __forceinline__ uint32_t pack2_sat(float a, float b) {
+  uint32_t r;
+  if (F16) {
+    if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  } else {
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  }
+  return r;
 }
 template <bool F16> __device__ __forceinline__ float2 unpack2(uint32_t u) {
   if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
@@ -242,7 +261,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;                               // [stages | num_kb][BN x 128 B]
   uint8_t* sOut = sB + (size_t)(p.b_resident ? num_kb : p.stages) * b_stage;        // [8 warps][2][32 rows x 64 B], SWIZZLE_64B
   uint8_t* sRes = sOut + (p.tma_epi ? 8 * TC_OUT_BUFS * TC_WARP_TILE : 0);          // [8 warps][nres][32 rows x 64 B]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (size_t)8 * p.nres * TC_WARP_TILE);
+  uint8_t* sEye = sRes;                                                             // res_kb: [64][128 B] identity, 128B-swizzled
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.res_kb ? (size_t)8192 : (size_t)8 * p.nres * TC_WARP_TILE));
   uint64_t* empty = full + 8;
   uint64_t* tmem_full = empty + 8;             // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
@@ -265,10 +285,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (p.res_kb && warp >= 2) {
+    // identity operand tile: row n holds 1.0 at element n; element k of a row lives in 16-byte chunk (k/8) ^ (n & 7)
+    const int t = (int)threadIdx.x - 64;                             // 0..255: four threads per row, two chunks each
+    const int n = t >> 2;
+    const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = (t & 3) * 2 + q;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (c == (n >> 3)) {
+        const int e = n & 7;
+        const uint32_t w = (e & 1) ? (one << 16) : one;
+        if ((e >> 1) == 0) v.x = w; else if ((e >> 1) == 1) v.y = w; else if ((e >> 1) == 2) v.z = w; else v.w = w;
+      }
+      *reinterpret_cast<uint4*>(sEye + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+    }
+    fence_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Everything above touched only shared memory / TMEM of this CTA.  From here on the previous kernel's output is read
+  // and buffers it may still be reading are overwritten: every role passes griddep_wait() first (the producer after
+  // requesting the weights, which no kernel writes).
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -279,6 +321,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_expect_tx(b_full, (uint32_t)num_kb * b_stage);
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + (size_t)kb * b_stage, &tmB, kb * TC_BK, n_tile * p.BN, b_full);
       }
+      griddep_wait();
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = p.b_resident ? TC_A_STAGE : TC_A_STAGE + b_stage;
       for (int i = 0; tile_at(p, i, m_tile, n_tile); ++i) {
@@ -293,6 +336,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
+        for (int j = 0; j < p.res_kb; ++j) {                     // residual slabs ride the same pipeline (A slot only)
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], TC_A_STAGE);
+          tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmRes, n0 + j * TC_BK, m0, &full[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -301,6 +350,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // instruction descriptor: D=f32, A=B=bf16 (1) or f16 (0), K-major both, N=BN, M=128
       const uint32_t fmt = F16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc_eye = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int m_tile, n_tile;
@@ -322,6 +372,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           umma_commit(&empty[stage]);                   // smem stage free once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        for (int j = 0; j < p.res_kb; ++j) {             // D[:, 64j .. 64j+63] += R_j x I
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
+          const uint64_t db = umma_desc(smem_u32(sEye));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u);
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
         umma_commit(&tmem_full[acc]);                   // accumulator complete
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
@@ -337,7 +398,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int row_in_tile = quad * 32 + lane;
     const int wslot = warp - 2;                                      // 0..7: private staging buffers / barriers per warp
     const bool elected = lane == 0;
-    const bool has_res = p.residual != nullptr;
+    griddep_wait();
+    const bool has_res = p.residual != nullptr && p.res_kb == 0;
     const int chunks_per_tile = (p.BN + 31) / 32;
     const int my_chunks = (chunks_per_tile - grp + 1) / 2;            // chunks grp, grp+2, ...
     const int nres = p.nres;                                         // residual buffers per warp (power of two)
@@ -412,19 +474,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               }
             }
           }
+          uint32_t pk[16];
           if (p.relu == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = F16 ? fminf(fmaxf(v[i], 0.f), 65504.f) : fmaxf(v[i], 0.f);
-          } else if (p.relu == 2) {
+            for (int i = 0; i < 16; ++i) pk[i] = pack2_sat<F16, true>(v[2 * i], v[2 * i + 1]);
+          } else {
+            if (p.relu == 2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { const float gl = apply_act(v[i], 2); v[i] = F16 ? fminf(fmaxf(gl, -65504.f), 65504.f) : gl; }
-          } else if (F16) {
+              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], 2);
+            }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -65504.f), 65504.f);
+            for (int i = 0; i < 16; ++i) pk[i] = pack2_sat<F16, false>(v[2 * i], v[2 * i + 1]);
           }
-          uint32_t pk[16];
+          if (zero_row) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = zero_row ? 0u : pack2_raw<F16>(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          }
           // gOut[obuf] was last read by this warp's store of chunk seq-2: retire it before overwriting
           if (elected) bulk_wait_read<1>();
           __syncwarp();
@@ -547,9 +612,11 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   const size_t b_stage = (size_t)pl->BN * TC_BK * 2;
   const int num_kb = a.ntaps * a.Cin_pad / TC_BK;
   const size_t budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers*/;
-  pl->nres = (pl->tma_epi && a.residual) ? 2 : 0;                  // residual buffers per epilogue group
+  pl->res_kb = (pl->tma_epi && a.residual && pl->BN % 64 == 0 && !getenv("YOLACT_B200_NO_RESMMA")) ? pl->BN / 64 : 0;
+  pl->nres = (pl->tma_epi && a.residual && !pl->res_kb) ? 2 : 0;   // residual buffers per epilogue group
   if (pl->nres) if (const char* e = getenv("YOLACT_B200_NRES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) pl->nres = v; }
   size_t epi_bytes = pl->tma_epi ? (size_t)8 * (TC_OUT_BUFS + pl->nres) * TC_WARP_TILE : 0;
+  if (pl->res_kb) epi_bytes += 8192;                               // identity operand tile
   // weight-resident mode: the whole [BN x Ktot] slice fits next to >= 3 A stages
   pl->b_resident = 0;
   pl->grid_mult = 1;
@@ -575,7 +642,10 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   if (s == YB_OK && pl->tma_epi) {
     const uint64_t out_rows = (uint64_t)max_batch * a.g.plane();
     s = make_map(&pl->tmOut, a.out, (uint64_t)a.Cout, out_rows, 32, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (s == YB_OK && a.residual) s = make_map(&pl->tmRes, a.residual, (uint64_t)a.Cout, out_rows, 32, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (s == YB_OK && a.residual) {
+      if (pl->res_kb) s = make_map(&pl->tmRes, a.residual, (uint64_t)a.Cout, out_rows, TC_BM, f16);   // A-operand slabs
+      else s = make_map(&pl->tmRes, a.residual, (uint64_t)a.Cout, out_rows, 32, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    }
   }
   if (s != YB_OK) { delete pl; return s; }
   static std::once_flag once;
@@ -601,7 +671,7 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
-  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident;
+  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
@@ -611,8 +681,16 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
     if (grid > total) grid = total;                           // total is a multiple of n_tiles
     if (grid < p.n_tiles) grid = p.n_tiles;
   }
-  if (p.is_f16) k_conv_tc<true><<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
-  else k_conv_tc<false><<<grid, TC_THREADS, pl->smem_bytes, s>>>(pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
+  static const bool pdl = getenv("YOLACT_B200_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  const cudaError_t le = p.is_f16 ? cudaLaunchKernelEx(&cfg, k_conv_tc<true>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p)
+                                  : cudaLaunchKernelEx(&cfg, k_conv_tc<false>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
+  YB_CHECK_CUDA(le);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
