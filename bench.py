@@ -246,6 +246,9 @@ def run_ours(args):
     host_np = [h.numpy() for h in host]
     for i in range(2):
         eng.detect_host(host_np[i & 1], p)
+    for i in range(3):                                                   # both pipeline slots: buffers, graphs, events
+        a_ = eng.submit_host(host_np[0], p); b_ = eng.submit_host(host_np[1], p)
+        eng.collect_host(a_); eng.collect_host(b_)
     if world > 1:
         dist.barrier()
     # pipelined public API: submit batch i+1 (its H2D copy overlaps the compute of batch i), then collect batch i

@@ -83,9 +83,18 @@ def test_conv_fp32_simt(cuda, shape):
     assert float((y - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize('pair', ['auto', 'single', 'pair', 'resmma', 'pair+resmma'])
 @pytest.mark.parametrize('precision', ['bf16', 'fp16'])
 @pytest.mark.parametrize('shape', SHAPES, ids=lambda s: 'B%d_Cin%d_H%d_Cout%d_k%d_s%d_relu%d_res%d' % s)
-def test_conv_tcgen05(cuda, shape, precision):
+def test_conv_tcgen05(cuda, shape, precision, pair, monkeypatch):
+    """`pair` forces the launch form of the tcgen05 kernel: one CTA per 128-row tile, or a CTA pair (cluster of 2,
+    cta_group::2 MMAs over both CTAs' operands) per 256-row tile; 'resmma' forces the residual-through-the-tensor-core
+    form (identity k-blocks) wherever the tile width allows; 'auto' is the per-layer choice the engine makes."""
+    if pair != 'auto':
+        monkeypatch.setenv('YOLACT_B200_PAIR', '1' if pair.startswith('pair') else '0')
+        monkeypatch.setenv('YOLACT_B200_RESMMA', '1' if pair.endswith('resmma') else '0')
+    if pair.endswith('resmma') and not shape[7]:
+        pytest.skip('no residual')
     B, Cin, H, Cout, k, stride, relu, res = shape
     x, w, b, r = conv_case(6, B, Cin, H, Cout, k, stride, res)
     prec, rnd, eps = (1, torch.bfloat16, 2.0 ** -8) if precision == 'bf16' else (2, torch.float16, 2.0 ** -11)
@@ -94,5 +103,6 @@ def test_conv_tcgen05(cuda, shape, precision):
     scale = max(1.0, float(ref.abs().max()))
     err = float((y_tc - ref).abs().max())
     assert err < 1.5 * eps * scale, (err, scale)          # only the final 16-bit rounding of the output
-    y_simt = run_conv(cuda, x, w, b, r, k, stride, relu, prec, 0)
-    assert float((y_tc - y_simt).abs().max()) < 1.5 * eps * scale       # same math on CUDA cores
+    if pair == 'auto':
+        y_simt = run_conv(cuda, x, w, b, r, k, stride, relu, prec, 0)
+        assert float((y_tc - y_simt).abs().max()) < 1.5 * eps * scale       # same math on CUDA cores

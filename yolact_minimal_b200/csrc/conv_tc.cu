@@ -56,7 +56,7 @@ struct TcParams {
 
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb;
+  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb, pair;
   size_t smem_bytes;
 };
 
@@ -101,6 +101,40 @@ __device__ __forceinline__ void epi_barrier(int grp) { asm volatile("bar.sync %0
 // memory is complete and visible (both are no-ops for a launch without the programmatic-serialization attribute)
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ---- CTA pair (cluster of 2, tcgen05 cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the pair -> the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -236,33 +270,42 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
 // CTA-local iteration i -> tile coordinates.  Streaming mode: tiles round-robin over the grid with
 // the N tiles of one M tile adjacent (A shared through L2).  Weight-resident mode: the CTA owns one
 // N tile for its whole life (its weights stay in shared memory) and strides over M tiles.
+template <bool PAIR>
 __device__ __forceinline__ bool tile_at(const TcParams& p, int i, int& m_tile, int& n_tile) {
+  // scheduling unit: one CTA, or one CTA pair (its M tile is 256 rows: 128 per CTA)
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // p.m_tiles counts unit tiles; the returned m_tile is THIS CTA's 128-row tile
   if (p.b_resident) {
-    n_tile = (int)blockIdx.x % p.n_tiles;
-    m_tile = (int)blockIdx.x / p.n_tiles + i * ((int)gridDim.x / p.n_tiles);
-    return m_tile < p.m_tiles;
+    n_tile = unit % p.n_tiles;
+    m_tile = unit / p.n_tiles + i * (units / p.n_tiles);
+    if (m_tile >= p.m_tiles) return false;
+  } else {
+    const int tile = unit + i * units;
+    if (tile >= p.m_tiles * p.n_tiles) return false;
+    m_tile = tile / p.n_tiles;
+    n_tile = tile - m_tile * p.n_tiles;
   }
-  const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-  if (tile >= p.m_tiles * p.n_tiles) return false;
-  m_tile = tile / p.n_tiles;
-  n_tile = tile - m_tile * p.n_tiles;
+  if (PAIR) m_tile = 2 * m_tile + (int)cluster_ctarank();
   return true;
 }
 
-template <bool F16>
+template <bool F16, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024B alignment
-  const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                              // CTA pair: 0 = leader (issues the MMAs)
+  const int bn_cta = PAIR ? p.BN / 2 : p.BN;                                        // weight rows held by this CTA
+  const uint32_t b_stage = (uint32_t)bn_cta * TC_BK * 2;
   const int num_kb = p.ntaps * p.kb_per_tap;
   uint8_t* sA = smem;                                                               // [stages][16 KiB]
   uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;                               // [stages | num_kb][BN x 128 B]
   uint8_t* sOut = sB + (size_t)(p.b_resident ? num_kb : p.stages) * b_stage;        // [8 warps][2][32 rows x 64 B], SWIZZLE_64B
   uint8_t* sRes = sOut + (p.tma_epi ? 8 * TC_OUT_BUFS * TC_WARP_TILE : 0);          // [8 warps][nres][32 rows x 64 B]
   uint8_t* sEye = sRes;                                                             // res_kb: [64][128 B] identity, 128B-swizzled
-  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.res_kb ? (size_t)8192 : (size_t)8 * p.nres * TC_WARP_TILE));
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.res_kb ? (size_t)8192 : (size_t)8 * p.nres * TC_WARP_TILE));   // pair: 32 identity rows per CTA
   uint64_t* empty = full + 8;
   uint64_t* tmem_full = empty + 8;             // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
@@ -277,34 +320,43 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 32; ++i) mbar_init(&res_full[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], PAIR ? 16 : 8); }   // pair: both CTAs' epilogue warps free the leader's accumulators
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (p.res_kb && warp >= 2) {
     // identity operand tile: row n holds 1.0 at element n; element k of a row lives in 16-byte chunk (k/8) ^ (n & 7)
+    // (pair: the N=64 identity is split like every B operand -- this CTA holds rows 32*rank .. 32*rank+31)
     const int t = (int)threadIdx.x - 64;                             // 0..255: four threads per row, two chunks each
-    const int n = t >> 2;
+    const int n = t >> 2;                                            // local row
+    const int kone = PAIR ? n + 32 * (int)rank : n;                  // column of the 1.0 in that row
     const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+    if (!PAIR || n < 32) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int c = (t & 3) * 2 + q;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (c == (n >> 3)) {
-        const int e = n & 7;
-        const uint32_t w = (e & 1) ? (one << 16) : one;
-        if ((e >> 1) == 0) v.x = w; else if ((e >> 1) == 1) v.y = w; else if ((e >> 1) == 2) v.z = w; else v.w = w;
+      for (int q = 0; q < 2; ++q) {
+        const int c = (t & 3) * 2 + q;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c == (kone >> 3)) {
+          const int e = kone & 7;
+          const uint32_t w = (e & 1) ? (one << 16) : one;
+          if ((e >> 1) == 0) v.x = w; else if ((e >> 1) == 1) v.y = w; else if ((e >> 1) == 2) v.z = w; else v.w = w;
+        }
+        *reinterpret_cast<uint4*>(sEye + n * 128 + ((c ^ (n & 7)) << 4)) = v;
       }
-      *reinterpret_cast<uint4*>(sEye + n * 128 + ((c ^ (n & 7)) << 4)) = v;
     }
     fence_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();               // pair: the peer's barriers / TMEM are ready too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // Everything above touched only shared memory / TMEM of this CTA.  From here on the previous kernel's output is read
@@ -316,46 +368,65 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ================= TMA producer =================
     if (lane == 0) {
       int m_tile, n_tile;
-      if (p.b_resident && tile_at(p, 0, m_tile, n_tile)) {
-        // the CTA's whole weight slice [BN x Ktot], loaded once
-        mbar_expect_tx(b_full, (uint32_t)num_kb * b_stage);
-        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + (size_t)kb * b_stage, &tmB, kb * TC_BK, n_tile * p.BN, b_full);
+      // pair: every load lands in the issuing CTA's own shared memory but is counted on the LEADER's barrier, which
+      // expects both CTAs' bytes (the leader's MMAs read both shared memories); each CTA recycles a stage on its own
+      // `empty` barrier (the MMA commit is multicast to both)
+      const uint32_t bfull_addr = PAIR ? map_to_rank(smem_u32(b_full), 0) : 0u;
+      if (p.b_resident && tile_at<PAIR>(p, 0, m_tile, n_tile)) {
+        // the CTA's whole weight slice [bn_cta x Ktot], loaded once
+        if (!PAIR || rank == 0) mbar_expect_tx(b_full, (uint32_t)num_kb * b_stage * (PAIR ? 2u : 1u));
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (PAIR) tma_load_2d_pair(sB + (size_t)kb * b_stage, &tmB, kb * TC_BK, n_tile * p.BN + (int)rank * bn_cta, bfull_addr);
+          else tma_load_2d(sB + (size_t)kb * b_stage, &tmB, kb * TC_BK, n_tile * p.BN, b_full);
+        }
       }
       griddep_wait();
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = p.b_resident ? TC_A_STAGE : TC_A_STAGE + b_stage;
-      for (int i = 0; tile_at(p, i, m_tile, n_tile); ++i) {
+      const uint32_t tx = (p.b_resident ? TC_A_STAGE : TC_A_STAGE + b_stage) * (PAIR ? 2u : 1u);
+      for (int i = 0; tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
         const int m0 = m_tile * TC_BM, n0 = n_tile * p.BN;
         for (int t = 0; t < p.ntaps; ++t) {
           const int row = m0 + p.tap_shift[t];
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], tx);
-            tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmA, kb * TC_BK, row, &full[stage]);
-            if (!p.b_resident) tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0, &full[stage]);
+            if (PAIR) {
+              const uint32_t full_addr = map_to_rank(smem_u32(&full[stage]), 0);
+              if (rank == 0) mbar_expect_tx(&full[stage], tx);
+              tma_load_2d_pair(sA + (size_t)stage * TC_A_STAGE, &tmA, kb * TC_BK, row, full_addr);
+              if (!p.b_resident) tma_load_2d_pair(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0 + (int)rank * bn_cta, full_addr);
+            } else {
+              mbar_expect_tx(&full[stage], tx);
+              tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmA, kb * TC_BK, row, &full[stage]);
+              if (!p.b_resident) tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0, &full[stage]);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
         for (int j = 0; j < p.res_kb; ++j) {                     // residual slabs ride the same pipeline (A slot only)
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], TC_A_STAGE);
-          tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmRes, n0 + j * TC_BK, m0, &full[stage]);
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * TC_A_STAGE);
+            tma_load_2d_pair(sA + (size_t)stage * TC_A_STAGE, &tmRes, n0 + j * TC_BK, m0, map_to_rank(smem_u32(&full[stage]), 0));
+          } else {
+            mbar_expect_tx(&full[stage], TC_A_STAGE);
+            tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmRes, n0 + j * TC_BK, m0, &full[stage]);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (pair: the leader CTA issues M=256 MMAs over both CTAs' operands) =================
+    if (lane == 0 && (!PAIR || rank == 0)) {
       // instruction descriptor: D=f32, A=B=bf16 (1) or f16 (0), K-major both, N=BN, M=128
       const uint32_t fmt = F16 ? 0u : 1u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t idesc_eye = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
+      const uint32_t idesc_eye = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int m_tile, n_tile;
-      if (p.b_resident && tile_at(p, 0, m_tile, n_tile)) mbar_wait(b_full, 0);
-      for (int i = 0; tile_at(p, i, m_tile, n_tile); ++i) {
+      if (p.b_resident && tile_at<PAIR>(p, 0, m_tile, n_tile)) mbar_wait(b_full, 0);
+      for (int i = 0; tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
@@ -367,9 +438,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);                   // smem stage free once these MMAs retire
+          if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);   // smem stage free (in both CTAs) once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         for (int j = 0; j < p.res_kb; ++j) {             // D[:, 64j .. 64j+63] += R_j x I
@@ -378,12 +450,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
           const uint64_t db = umma_desc(smem_u32(sEye));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u);
-          umma_commit(&empty[stage]);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            if (PAIR) umma_pair(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u);
+            else umma_bf16(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u);
+          }
+          if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);                   // accumulator complete
+        if (PAIR) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);   // accumulator complete (each CTA holds its 128 rows)
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
@@ -411,19 +485,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int seq = 0;                                                     // warp-local chunk sequence over all tiles
     // residual prefetch cursor: next (tile iteration, local chunk) to request
     int pf_it = 0, pf_j = 0, pf_seq = 0, pf_mt = 0, pf_nt = 0;
-    bool pf_ok = p.tma_epi && has_res && my_chunks > 0 && tile_at(p, 0, pf_mt, pf_nt);
+    bool pf_ok = p.tma_epi && has_res && my_chunks > 0 && tile_at<PAIR>(p, 0, pf_mt, pf_nt);
     auto issue_res_load = [&]() {
       const int buf = pf_seq & (nres - 1);
       mbar_expect_tx(&gres_full[buf], TC_WARP_TILE);
       tma_load_2d(gRes + buf * TC_WARP_TILE, &tmRes, pf_nt * p.BN + (2 * pf_j + grp) * 32, pf_mt * TC_BM + quad * 32, &gres_full[buf]);
       ++pf_seq;
-      if (++pf_j == my_chunks) { pf_j = 0; ++pf_it; pf_ok = tile_at(p, pf_it, pf_mt, pf_nt); }
+      if (++pf_j == my_chunks) { pf_j = 0; ++pf_it; pf_ok = tile_at<PAIR>(p, pf_it, pf_mt, pf_nt); }
     };
     if (elected) {
       for (int q = 0; q < nres && pf_ok; ++q) issue_res_load();
     }
     int m_tile, n_tile;
-    for (int it = 0; tile_at(p, it, m_tile, n_tile); ++it) {
+    for (int it = 0; tile_at<PAIR>(p, it, m_tile, n_tile); ++it) {
       const long long m = (long long)m_tile * TC_BM + row_in_tile;
       const bool valid = m < p.M;
       int img = 0, y = 0, x = 0;
@@ -522,17 +596,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(map_to_rank(smem_u32(&tmem_empty[acc]), 0)); else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (p.tma_epi && elected) bulk_wait<0>();                     // all output tiles landed before the CTA exits
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();               // pair: neither CTA leaves while the other still uses its smem / TMEM / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -609,10 +686,23 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   while (cols < 2 * pl->BN) cols <<= 1;
   pl->tmem_cols = cols;
   pl->tma_epi = (a.out_mode == 0 && pl->BN % 32 == 0) ? 1 : 0;
-  const size_t b_stage = (size_t)pl->BN * TC_BK * 2;
+  // CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each CTA stages its own 128 A rows and HALF of the
+  // weight tile
+  // -- a third less shared-memory fill per MMA than two independent CTAs.  Measured per layer (profiles/r1_pair_vs_single.txt): a
+  // win of 5-12 % where the layer is operand-fill bound (K >= 1024 with the full 256-wide N tile: the 3x3 and the
+  // 1024/2048-channel reduce convs), a loss where the epilogue or HBM bounds it (the pair advances at the pace of its slower
+  // CTA), so only the former use it.  YOLACT_B200_PAIR=0 / 1 forces it off / on for every eligible (BN % 32 == 0) layer.
+  pl->pair = (pl->BN == 256 && a.ntaps * a.Cin_pad >= 1024) ? 1 : 0;
+  if (const char* e = getenv("YOLACT_B200_PAIR")) pl->pair = (atoi(e) != 0 && pl->BN % 32 == 0) ? 1 : 0;
+  const size_t b_stage = (size_t)(pl->pair ? pl->BN / 2 : pl->BN) * TC_BK * 2;
   const int num_kb = a.ntaps * a.Cin_pad / TC_BK;
   const size_t budget = 227 * 1024 - 1024 /*align*/ - 1024 /*barriers*/;
-  pl->res_kb = (pl->tma_epi && a.residual && pl->BN % 64 == 0 && !getenv("YOLACT_B200_NO_RESMMA")) ? pl->BN / 64 : 0;
+  // residual through the tensor core: measured in the network it pays for the short-K expand convs (64->256 @138: -8 %, 128->512 @69:
+  // -18 %) whose epilogue is the bottleneck, and costs 4-20 % once K >= 256, where the extra A-slab stages compete with the main
+  // k-blocks for the few pipeline stages.  YOLACT_B200_RESMMA=0 / 1 forces it off / on.
+  bool res_mma = a.ntaps * a.Cin_pad <= 128;
+  if (const char* e = getenv("YOLACT_B200_RESMMA")) res_mma = atoi(e) != 0;
+  pl->res_kb = (pl->tma_epi && a.residual && pl->BN % 64 == 0 && res_mma) ? pl->BN / 64 : 0;
   pl->nres = (pl->tma_epi && a.residual && !pl->res_kb) ? 2 : 0;   // residual buffers per epilogue group
   if (pl->nres) if (const char* e = getenv("YOLACT_B200_NRES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) pl->nres = v; }
   size_t epi_bytes = pl->tma_epi ? (size_t)8 * (TC_OUT_BUFS + pl->nres) * TC_WARP_TILE : 0;
@@ -637,7 +727,7 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
   int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.in_row_stride);
-  if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)pl->BN, f16);
+  if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN), f16);
   pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;                      // placeholders when the TMA epilogue is off
   if (s == YB_OK && pl->tma_epi) {
     const uint64_t out_rows = (uint64_t)max_batch * a.g.plane();
@@ -651,8 +741,10 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { delete pl; set_error("cudaFuncSetAttribute(k_conv_tc) failed: %s", cudaGetErrorString(attr_err)); return YB_ERR_CUDA; }
   *out = pl;
@@ -664,7 +756,8 @@ void tc_plan_destroy(TcPlan* p) { delete p; }
 int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   TcParams p;
   p.M = (long long)a.B * a.g.plane();
-  p.m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
+  const int unit_rows = pl->pair ? 2 * TC_BM : TC_BM;
+  p.m_tiles = (int)((p.M + unit_rows - 1) / unit_rows);            // tiles per scheduling unit (CTA or CTA pair)
   p.n_tiles = a.Cout_pad / pl->BN;
   p.kb_per_tap = a.Cin_pad / TC_BK;
   p.ntaps = a.ntaps;
@@ -675,21 +768,35 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
-  int grid = total < sms ? total : sms;
+  const int max_units = pl->pair ? sms / 2 : sms;
+  int units = total < max_units ? total : max_units;
   if (pl->b_resident) {
-    grid = sms / p.n_tiles * p.n_tiles;                       // whole groups of N tiles
-    if (grid > total) grid = total;                           // total is a multiple of n_tiles
-    if (grid < p.n_tiles) grid = p.n_tiles;
+    units = max_units / p.n_tiles * p.n_tiles;                // whole groups of N tiles
+    if (units > total) units = total;                         // total is a multiple of n_tiles
+    if (units < p.n_tiles) units = p.n_tiles;
   }
+  const int grid = pl->pair ? 2 * units : units;
   static const bool pdl = getenv("YOLACT_B200_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  const cudaError_t le = p.is_f16 ? cudaLaunchKernelEx(&cfg, k_conv_tc<true>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p)
-                                  : cudaLaunchKernelEx(&cfg, k_conv_tc<false>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pl->pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  cudaError_t le;
+  if (pl->pair) le = p.is_f16 ? cudaLaunchKernelEx(&cfg, k_conv_tc<true, true>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p)
+                              : cudaLaunchKernelEx(&cfg, k_conv_tc<false, true>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
+  else le = p.is_f16 ? cudaLaunchKernelEx(&cfg, k_conv_tc<true, false>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p)
+                     : cudaLaunchKernelEx(&cfg, k_conv_tc<false, false>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
   YB_CHECK_CUDA(le);
   YB_CHECK_LAUNCH();
   return YB_OK;
