@@ -5,8 +5,10 @@ import numpy as np, torch
 from yolact_minimal_b200 import _lib
 LAYERS = {  # name: (B, Cin, H, Cout, k, stride, relu, residual)
     'expand35': (64, 256, 35, 1024, 1, 1, 1, 1),
+    'expand35_nores': (64, 256, 35, 1024, 1, 1, 1, 0),
     'expand138': (64, 64, 138, 256, 1, 1, 1, 1),
     'expand69': (64, 128, 69, 512, 1, 1, 1, 1),
+    'expand18': (64, 512, 18, 2048, 1, 1, 1, 1),
     'reduce35': (64, 1024, 35, 256, 1, 1, 1, 0),
     'c3x3_35': (64, 256, 35, 256, 3, 1, 1, 0),
     'c3x3_64_138': (64, 64, 138, 64, 3, 1, 1, 0),
