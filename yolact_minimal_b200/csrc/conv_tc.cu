@@ -29,6 +29,8 @@ constexpr int TC_THREADS = 320;             // TMA warp, MMA warp, 2 x 4 epilogu
 constexpr int TC_OUT_BUFS = 2;                // output staging buffers per epilogue warp
 constexpr uint32_t TC_WARP_TILE = 32 * 32 * 2;  // 2 KiB: one warp's 32 rows x 32 columns of 16-bit outputs
 constexpr uint32_t TC_A_STAGE = TC_BM * TC_BK * 2;   // 16 KiB
+constexpr uint32_t TC_SLAB_ROWS = TC_BM + 2;         // slab mode: rows m0-1 .. m0+128 of one tap row
+constexpr uint32_t TC_A_SLAB = 136 * TC_BK * 2;      // 17 KiB slot: the 130-row slab padded to the 1 KiB swizzle period
 constexpr uint32_t TC_EPI_TILE = TC_BM * 32 * 2;     // 8 KiB: 128 rows x 32 columns of 16-bit outputs
 
 struct TcParams {
@@ -45,6 +47,10 @@ struct TcParams {
   int tma_epi;            // out_mode 0 && BN % 32 == 0: smem-staged TMA stores (+ TMA-prefetched residual)
   int nres;               // residual prefetch buffers (0 if none)
   int b_resident;         // weights of the CTA's N tile stay in shared memory for all its M tiles
+  int slab, stages_a;     // slab: 3x3 stride-1 convs load ONE [130 x 64] A slab per (tap row, k-block) and run the three dx taps off
+                          // it through descriptors that start 0 / 128 / 256 B into the slab (UMMA swizzles on absolute shared-memory
+                          // address bits, so a row-shifted start needs no base offset -- tools/dbg_slab.py).  A third of the A
+                          // traffic; the slab ring (stages_a slots of 17 KB) and the weight ring (stages) then advance separately.
   int res_kb;             // > 0: the residual is added BY THE TENSOR CORE: BN/64 extra k-blocks whose A tile is the
                           // residual's [128 x 64] slab and whose B tile is a shared-memory 64x64 identity (N=64 MMAs
                           // into the matching 64 accumulator columns) -- the epilogue never touches the residual
@@ -56,7 +62,7 @@ struct TcParams {
 
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb, pair;
+  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb, pair, slab, stages_a;
   size_t smem_bytes;
 };
 
@@ -301,7 +307,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t b_stage = (uint32_t)bn_cta * TC_BK * 2;
   const int num_kb = p.ntaps * p.kb_per_tap;
   uint8_t* sA = smem;                                                               // [stages][16 KiB]
-  uint8_t* sB = smem + (size_t)p.stages * TC_A_STAGE;                               // [stages | num_kb][BN x 128 B]
+  uint8_t* sB = smem + (p.slab ? (size_t)p.stages_a * TC_A_SLAB : (size_t)p.stages * TC_A_STAGE);   // [stages | num_kb][BN x 128 B]
   uint8_t* sOut = sB + (size_t)(p.b_resident ? num_kb : p.stages) * b_stage;        // [8 warps][2][32 rows x 64 B], SWIZZLE_64B
   uint8_t* sRes = sOut + (p.tma_epi ? 8 * TC_OUT_BUFS * TC_WARP_TILE : 0);          // [8 warps][nres][32 rows x 64 B]
   uint8_t* sEye = sRes;                                                             // res_kb: [64][128 B] identity, 128B-swizzled
@@ -311,14 +317,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint64_t* res_full = tmem_empty + 2;         // [8 warps][4]
   uint64_t* b_full = res_full + 32;            // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* full_a = b_full + 1;               // [8] slab ring (slab mode)
+  uint64_t* empty_a = full_a + 8;              // [8]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(empty_a + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < 32; ++i) mbar_init(&res_full[i], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], PAIR ? 16 : 8); }   // pair: both CTAs' epilogue warps free the leader's accumulators
     mbar_init(b_full, 1);
@@ -383,7 +391,38 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       griddep_wait();
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = (p.b_resident ? TC_A_STAGE : TC_A_STAGE + b_stage) * (PAIR ? 2u : 1u);
-      for (int i = 0; tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
+      int sa = 0; uint32_t phase_a = 0;
+      for (int i = 0; p.slab && tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
+        // slab mode: per (tap row dy, k-block) one A slab, then the three dx weight tiles that consume it
+        const int m0 = m_tile * TC_BM, n0 = n_tile * p.BN;
+        for (int dy = 0; dy < 3; ++dy) {
+          const int row = m0 + p.tap_shift[3 * dy];
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(&empty_a[sa], phase_a ^ 1);
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * TC_SLAB_ROWS * 128);
+              tma_load_2d_pair(sA + (size_t)sa * TC_A_SLAB, &tmA, kb * TC_BK, row, map_to_rank(smem_u32(&full_a[sa]), 0));
+            } else {
+              mbar_expect_tx(&full_a[sa], TC_SLAB_ROWS * 128);
+              tma_load_2d(sA + (size_t)sa * TC_A_SLAB, &tmA, kb * TC_BK, row, &full_a[sa]);
+            }
+            if (++sa == p.stages_a) { sa = 0; phase_a ^= 1; }
+            for (int dx = 0; dx < 3 && !p.b_resident; ++dx) {
+              const int kcol = ((3 * dy + dx) * p.kb_per_tap + kb) * TC_BK;
+              mbar_wait(&empty[stage], phase ^ 1);
+              if (PAIR) {
+                if (rank == 0) mbar_expect_tx(&full[stage], 2 * b_stage);
+                tma_load_2d_pair(sB + (size_t)stage * b_stage, &tmB, kcol, n0 + (int)rank * bn_cta, map_to_rank(smem_u32(&full[stage]), 0));
+              } else {
+                mbar_expect_tx(&full[stage], b_stage);
+                tma_load_2d(sB + (size_t)stage * b_stage, &tmB, kcol, n0, &full[stage]);
+              }
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+      for (int i = 0; !p.slab && tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
         const int m0 = m_tile * TC_BM, n0 = n_tile * p.BN;
         for (int t = 0; t < p.ntaps; ++t) {
           const int row = m0 + p.tap_shift[t];
@@ -423,6 +462,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       const uint32_t idesc_eye = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
+      int sa = 0; uint32_t phase_a = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int m_tile, n_tile;
       if (p.b_resident && tile_at<PAIR>(p, 0, m_tile, n_tile)) mbar_wait(b_full, 0);
@@ -430,7 +470,33 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        if (p.slab) {
+          int kbi = 0;
+          for (int dy = 0; dy < 3; ++dy) {
+            for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+              mbar_wait(&full_a[sa], phase_a);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(sA + (size_t)sa * TC_A_SLAB);
+              for (int dx = 0; dx < 3; ++dx, ++kbi) {
+                if (!p.b_resident) { mbar_wait(&full[stage], phase); tc_fence_after(); }
+                const uint64_t da = umma_desc(a_addr + (uint32_t)dx * 128u);         // tap dx = slab rows dx .. dx+127
+                const uint64_t db = umma_desc(smem_u32(sB + (size_t)(p.b_resident ? (3 * dy + dx) * p.kb_per_tap + kb : stage) * b_stage));
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+                  else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+                }
+                if (!p.b_resident) {
+                  if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+                  if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+              }
+              if (PAIR) umma_commit_pair(&empty_a[sa]); else umma_commit(&empty_a[sa]);   // slab consumed by all three taps
+              if (++sa == p.stages_a) { sa = 0; phase_a ^= 1; }
+            }
+          }
+        }
+        for (int kb = 0; kb < num_kb && !p.slab; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
@@ -711,17 +777,34 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   if (pl->nres) if (const char* e = getenv("YOLACT_B200_NRES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) pl->nres = v; }
   size_t epi_bytes = pl->tma_epi ? (size_t)8 * (TC_OUT_BUFS + pl->nres) * TC_WARP_TILE : 0;
   if (pl->res_kb) epi_bytes += 8192;                               // identity operand tile
+  // slab mode (3x3, stride 1: the three dx taps of a tap row are consecutive rows of the same matrix)
+  pl->slab = (a.ntaps == 9 && !pl->res_kb && !getenv("YOLACT_B200_NO_SLAB")) ? 1 : 0;
+  for (int dy = 0; dy < 3 && pl->slab; ++dy)
+    for (int dx = 1; dx < 3; ++dx)
+      if (a.tap_shift[3 * dy + dx] != a.tap_shift[3 * dy] + dx) pl->slab = 0;
+  pl->stages_a = 0;
+  const size_t a_slot = pl->slab ? TC_A_SLAB : TC_A_STAGE;
   // weight-resident mode: the whole [BN x Ktot] slice fits next to >= 3 A stages
   pl->b_resident = 0;
   pl->grid_mult = 1;
   const int n_tiles = a.Cout_pad / pl->BN;
-  if (!getenv("YOLACT_B200_NO_BRES") && (size_t)num_kb * b_stage + epi_bytes + 3 * TC_A_STAGE <= budget && n_tiles <= 64) {
+  if (!getenv("YOLACT_B200_NO_BRES") && (size_t)num_kb * b_stage + epi_bytes + 3 * a_slot <= budget && n_tiles <= 64) {
     pl->b_resident = 1;
     pl->grid_mult = n_tiles;
-    int stages = (int)((budget - epi_bytes - (size_t)num_kb * b_stage) / TC_A_STAGE);
-    pl->stages = stages > 8 ? 8 : stages;
-    pl->smem_bytes = (size_t)pl->stages * TC_A_STAGE + (size_t)num_kb * b_stage + epi_bytes + 1024 + 1024;
-  } else {
+    int stages = (int)((budget - epi_bytes - (size_t)num_kb * b_stage) / a_slot);
+    stages = stages > 8 ? 8 : stages;
+    if (pl->slab) { pl->stages_a = stages; pl->stages = 1; } else pl->stages = stages;
+    pl->smem_bytes = (size_t)stages * a_slot + (size_t)num_kb * b_stage + epi_bytes + 1024 + 1024;
+  } else if (pl->slab) {
+    // separate rings: 3 slabs (= 9 k-blocks of look-ahead on the A side), the rest of the budget for weight tiles
+    pl->stages_a = 3;
+    int stages = (int)((budget - epi_bytes - 3 * a_slot) / b_stage);
+    if (stages > 8) { stages = 8; pl->stages_a = (int)((budget - epi_bytes - 8 * b_stage) / a_slot); if (pl->stages_a > 8) pl->stages_a = 8; }
+    pl->stages = stages;
+    pl->smem_bytes = (size_t)pl->stages_a * a_slot + (size_t)stages * b_stage + epi_bytes + 1024 + 1024;
+    if (stages < 3) { pl->slab = 0; pl->stages_a = 0; }
+  }
+  if (!pl->b_resident && !pl->slab) {
     const size_t per_stage = TC_A_STAGE + b_stage;
     int stages = (int)((budget - epi_bytes) / per_stage);
     pl->stages = stages > 8 ? 8 : stages;
@@ -730,7 +813,7 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   const int Ktot = a.ntaps * a.Cin_pad;
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
-  int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.in_row_stride);
+  int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, pl->slab ? TC_SLAB_ROWS : TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.in_row_stride);
   if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN), f16);
   pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;                      // placeholders when the TMA epilogue is off
   if (s == YB_OK && pl->tma_epi) {
@@ -768,7 +851,7 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
-  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb;
+  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
