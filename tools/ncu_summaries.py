@@ -13,8 +13,8 @@ def launch_list(path, out):
         agg[name][0] += 1; agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
     with open(out, 'w') as o:
-        o.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none -s 447 -c 300 python bench.py --steps 2 --warmup 3\n')
-        o.write(f'# window = the 2 timed steps (cold-cache, serialised launches: compare SHARES, not absolutes)\n')
+        o.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed/" python bench.py --steps 2 --warmup 3\n')
+        o.write(f'# window = the 2 timed steps (NVTX range pushed by bench.py; cold-cache, serialised launches: compare SHARES, not absolutes)\n')
         o.write(f'# {len(rows)} launches, {tot:.1f} us total\n')
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             o.write('%-48s n=%4d  us=%10.1f  share=%.3f\n' % (k[:48], v[0], v[1], v[1] / tot))
@@ -44,6 +44,6 @@ def full(path, out, title):
 
 if __name__ == '__main__':
     launch_list('gpurun_out/r1_launches.csv', 'profiles/r1_ncu_launch_list_bench.txt')
-    full('gpurun_out/r1_prof_conv_tc.ncu-rep', 'profiles/r1_ncu_conv_tc_bench.txt', 'k_conv_tc inside bench.py (launches 331..336 of the kernel: layer2/layer3 boundary)')
+    full('gpurun_out/r1_prof_conv_tc.ncu-rep', 'profiles/r1_ncu_conv_tc_bench.txt',
+         'k_conv_tc inside bench.py: launches 28..33 of the timed steps = two layer3 bottlenecks (1x1 1024->256 [pair], 3x3 256->256 [pair+slab], 1x1 256->1024 +residual)')
     full('gpurun_out/r1_prof_post.ncu-rep', 'profiles/r1_ncu_postprocess_bench.txt', 'post-process kernels inside bench.py (res101@550 network output, B=64)')
-    full('gpurun_out/prof_expand35_v3.ncu-rep', 'profiles/r1_ncu_conv_tc_expand35.txt', 'k_conv_tc, 1x1 256->1024 @35x35 + residual + ReLU, B=64 (tools/prof_layer.py expand35), before the instruction diet')

@@ -5,7 +5,7 @@ agg = collections.OrderedDict()
 for r in rows:
     a = agg.setdefault(int(r['op']), dict(r, ms=0.0, n=0))
     a['ms'] += float(r['ms']); a['n'] += 1
-KIND = {0: 'stem(im2col+gemm)', 1: 'maxpool', 2: 'phase_split', 4: 'upsample_add', 5: 'upsample2x', 6: 'head_finalize'}
+KIND = {0: 'stem(s2d+conv_tc)', 1: 'maxpool', 2: 'phase_split', 4: 'upsample_add', 5: 'upsample2x', 6: 'head_finalize'}
 groups = collections.OrderedDict()
 for a in agg.values():
     ms = a['ms'] / a['n']

@@ -49,7 +49,7 @@ struct TcParams {
   int b_resident;         // weights of the CTA's N tile stay in shared memory for all its M tiles
   int slab, stages_a;     // slab: 3x3 stride-1 convs load ONE [130 x 64] A slab per (tap row, k-block) and run the three dx taps off
                           // it through descriptors that start 0 / 128 / 256 B into the slab (UMMA swizzles on absolute shared-memory
-                          // address bits, so a row-shifted start needs no base offset -- tools/dbg_slab.py).  A third of the A
+                          // address bits, so a row-shifted start needs no base offset: probed once, and every 3x3 parity test runs through it).  A third of the A
                           // traffic; the slab ring (stages_a slots of 17 KB) and the weight ring (stages) then advance separately.
   int res_kb;             // > 0: the residual is added BY THE TENSOR CORE: BN/64 extra k-blocks whose A tile is the
                           // residual's [128 x 64] slab and whose B tile is a shared-memory 64x64 identity (N=64 MMAs

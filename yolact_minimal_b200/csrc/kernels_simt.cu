@@ -209,55 +209,6 @@ __global__ void __launch_bounds__(256) k_stem(const float* __restrict__ img, con
   }
 }
 
-// 16-bit modes: the stem runs on the tensor cores as a GEMM with K = 7*7*3 = 147 padded to 192.
-// This kernel writes the im2col rows in the haloed geometry of the stem OUTPUT:
-// cols[(b, yp, xp)][k], k = (r*7+s)*3 + ci  <- img[b, ci, 2(yp-1)+r-3, 2(xp-1)+s-3]  (0 outside / halo / k >= 147)
-constexpr int kStemK = 152;                      // 7*7*3 = 147 rounded up to a multiple of 8 (16-byte TMA rows)
-constexpr int IC_PX = 64;                       // output pixels per block (one haloed row segment)
-constexpr int IC_W = 2 * IC_PX + 6;             // staged input columns (134)
-template <typename T>
-__global__ void __launch_bounds__(256) k_stem_im2col(const float* __restrict__ img, T* __restrict__ cols, int B, int S, int H1) {
-  constexpr int KP = kStemK, N = 8, KV = KP / N;
-  __shared__ float s_in[3][7][IC_W + 2];
-  const int Hp = H1 + 2;
-  const int b = blockIdx.z, yp = blockIdx.y, xp0 = blockIdx.x * IC_PX, tid = threadIdx.x;
-  const bool row_valid = yp >= 1 && yp <= H1;
-  if (row_valid) {
-    const int iy0 = 2 * (yp - 1) - 3, ix0 = 2 * (xp0 - 1) - 3;
-    for (int i = tid; i < 3 * 7 * IC_W; i += 256) {
-      const int q = i % IC_W, rr = (i / IC_W) % 7, ci = i / (IC_W * 7);
-      const int iy = iy0 + rr, ix = ix0 + q;
-      float v = 0.f;
-      if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = __ldg(img + (((size_t)b * 3 + ci) * S + iy) * S + ix);
-      s_in[ci][rr][q] = v;
-    }
-  }
-  __syncthreads();
-  T* orow = cols + ((size_t)b * Hp + yp) * Hp * KP;
-  for (int item = tid; item < IC_PX * KV; item += 256) {
-    const int px = item / KV, kv = item - px * KV;
-    const int xp = xp0 + px;
-    if (xp >= Hp) break;
-    float v[N];
-#pragma unroll
-    for (int e = 0; e < N; ++e) {
-      const int k = kv * N + e;
-      const int tap = k / 3, ci = k - tap * 3, rr = tap / 7, ss = tap - rr * 7;
-      v[e] = (row_valid && xp >= 1 && xp <= H1 && k < 147) ? s_in[ci][rr][2 * px + ss] : 0.f;
-    }
-    VecIO<T>::store(orow + (size_t)xp * KP + kv * N, v);
-  }
-}
-
-int launch_stem_im2col(const float* img, void* cols, int dt, int B, int S, int H1, cudaStream_t s) {
-  YB_REQUIRE(dt != DT_F32, YB_ERR_INVALID, "stem_im2col is for the 16-bit modes");
-  dim3 grid(ceil_div(H1 + 2, IC_PX), H1 + 2, B);
-  if (dt == DT_BF16) k_stem_im2col<__nv_bfloat16><<<grid, 256, 0, s>>>(img, (__nv_bfloat16*)cols, B, S, H1);
-  else k_stem_im2col<__half><<<grid, 256, 0, s>>>(img, (__half*)cols, B, S, H1);
-  YB_CHECK_LAUNCH();
-  return YB_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
 // stem, 16-bit modes: space-to-depth repack.  The 7x7 stride-2 convolution over 3 channels equals a 4x4
 // stride-1 convolution over the 12 channels (py, px, ci) of the 2x2 space-to-depth image (one all-zero tap

@@ -68,7 +68,6 @@ int launch_stem(const float* img_nchw, const float* w /*[7][7][3][64]*/, const f
                 int B, int S, int H1, cudaStream_t s);
 int launch_stem_s2d(const float* img_nchw, void* out /*[B][(H1+2)^2][16 | 64]*/, int dt, int wide, int B, int S, int H1, cudaStream_t s);
 bool tc_overlapping_rows_ok();   // can the driver encode a tensor map whose rows overlap (row stride < row length)?
-int launch_stem_im2col(const float* img_nchw, void* cols /*[B*(H1+2)^2][192]*/, int dt, int B, int S, int H1, cudaStream_t s);
 int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s);
 int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
                        long long plane_stride_rows, cudaStream_t s);

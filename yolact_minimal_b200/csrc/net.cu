@@ -51,7 +51,7 @@ struct Op {
   int conv = -1;               // index into convs
   int stride = 1, relu = 0, out_mode = 0, ext = EXT_NONE;
   int level = 0;               // head level
-  int aux = -1;                // extra scratch activation (stem: im2col rows)
+  int aux = -1;                // extra scratch activation (stem: space-to-depth image)
   std::string p0, p1, p2;      // Swin ops: parameter names (LayerNorm weight/bias; attention: qkv bias, rel-pos table)
   int heads = 0, shift = 0;    // attention
   TcPlan* tc = nullptr;
