@@ -1,19 +1,33 @@
-// tcgen05 implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+// tcgen05 implicit-GEMM convolution for sm_100a (fp16 / bf16 operands, fp32 accumulation in TMEM).
 //
 //   out[M, Cout] = epilogue( sum_{tap} A[M + shift_tap, Cin] * W_tap[Cin, Cout] )
 //
 // on the haloed NHWC layout of layers.cuh, where every convolution tap is a constant row shift
-// of the activation matrix.  Persistent, warp-specialised CTA (192 threads, 1 CTA / SM):
+// of the activation matrix.  Persistent, warp-specialised CTA (320 threads, 1 CTA / SM):
 //   warp 0      TMA producer: per k-block one 128x64 A tile (row coordinate m0 + shift_tap,
 //               out-of-range rows zero-filled by TMA = the conv padding) and one BNx64 weight
-//               tile, both 128B-swizzled, into a ring of shared-memory stages (mbarrier full/empty)
+//               tile, both 128B-swizzled, into a ring of shared-memory stages (mbarrier full/empty);
+//               small-K layers keep their whole weight slice resident instead
 //   warp 1      allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16) from one elected lane,
 //               tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2..9  epilogue (two groups of four warps, alternating 32-column chunks): tcgen05.ld the 128xBN fp32 accumulator (double-buffered in TMEM so the
-//               next tile's MMAs overlap), + folded-BN bias, + residual, ReLU, halo zeroing,
-//               bf16 (or dense fp32) stores
+//   warps 2..9  eight independent epilogue warps (two per TMEM lane quadrant, alternating 32-column
+//               chunks): tcgen05.ld of the fp32 accumulator (double-buffered in TMEM so the next tile's
+//               MMAs overlap), + folded-BN bias, + residual, ReLU/clamp/pack, halo zeroing, swizzled
+//               smem staging and one TMA store per warp and chunk (or dense fp32 stores)
 // Tiles are scheduled round-robin over the persistent grid, N-tiles of one M-tile adjacent so
 // the A tile is shared through L2.
+//
+// Per-layer forms chosen in tc_plan_create (measurements: profiles/r1_conv_tc_experiments.txt):
+//   PAIR      cluster of two CTAs, tcgen05 cta_group::2: one 256 x BN tile per pair, each CTA stages its
+//             own 128 A rows and half of the weight tile; the leader (rank 0) issues the MMAs
+//   slab      3x3 stride 1: one [130 x 64] A slab per (tap row, k-block) serves the three dx taps through
+//             row-shifted shared-memory descriptors; slab ring and weight ring advance separately
+//   res_kb    residual added by the tensor core: BN/64 extra k-blocks against an identity tile
+// Launches use programmatic dependent launch: everything before griddep_wait() touches only this
+// CTA's shared memory / TMEM (and the constant weights), so it overlaps the previous kernel's tail.
+//
+// Environment switches (tooling / A-B runs only): YOLACT_B200_PAIR=0|1, YOLACT_B200_RESMMA=0|1,
+// YOLACT_B200_NO_SLAB, YOLACT_B200_NO_BRES, YOLACT_B200_NO_PDL, YOLACT_B200_BN=<n>, YOLACT_B200_NRES=<n>.
 #include "layers.cuh"
 
 #include <cuda.h>
