@@ -132,7 +132,9 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): the TMEM hand-off is ordered by the
+  // tcgen05 fences on both sides; a .release.cluster arrive costs a MEMBAR.ALL.GPU per epilogue warp and tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose bytes are counted on a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
@@ -771,12 +773,13 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   pl->tmem_cols = cols;
   pl->tma_epi = (a.out_mode == 0 && pl->BN % 32 == 0) ? 1 : 0;
   // CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each CTA stages its own 128 A rows and HALF of the
-  // weight tile
-  // -- a third less shared-memory fill per MMA than two independent CTAs.  Measured per layer (profiles/r1_pair_vs_single.txt): a
-  // win of 5-12 % where the layer is operand-fill bound (K >= 1024 with the full 256-wide N tile: the 3x3 and the
-  // 1024/2048-channel reduce convs), a loss where the epilogue or HBM bounds it (the pair advances at the pace of its slower
-  // CTA), so only the former use it.  YOLACT_B200_PAIR=0 / 1 forces it off / on for every eligible (BN % 32 == 0) layer.
-  pl->pair = (pl->BN == 256 && a.ntaps * a.Cin_pad >= 1024) ? 1 : 0;
+  // weight tile -- a third less L2 -> shared-memory fill per MMA than two independent CTAs, and a half-size resident weight
+  // slice.  Measured per layer (profiles/r1_pair_vs_single.txt, r1_conv_tc_experiments.txt): -5..-12 % where the layer is
+  // fill-bound (K >= 1024 with the full 256-wide N tile: the 3x3 and the 1024/2048-channel reduce convs) and -5..-19 % on the
+  // 256-wide expand convs with a residual (resident half slice + deep slab ring); neutral or slightly worse elsewhere (the pair
+  // advances at the pace of its slower CTA).  YOLACT_B200_PAIR=0 / 1 forces it off / on for every eligible (BN % 32 == 0) layer.
+  const int ktot = a.ntaps * a.Cin_pad;
+  pl->pair = (pl->BN == 256 && (ktot >= 1024 || (a.residual && a.out_mode == 0 && ktot >= 256))) ? 1 : 0;
   if (const char* e = getenv("YOLACT_B200_PAIR")) pl->pair = (atoi(e) != 0 && pl->BN % 32 == 0) ? 1 : 0;
   const size_t b_stage = (size_t)(pl->pair ? pl->BN / 2 : pl->BN) * TC_BK * 2;
   const int num_kb = a.ntaps * a.Cin_pad / TC_BK;
@@ -784,7 +787,9 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   // residual through the tensor core: measured in the network it pays for the short-K expand convs (64->256 @138: -8 %, 128->512 @69:
   // -18 %) whose epilogue is the bottleneck, and costs 4-20 % once K >= 256, where the extra A-slab stages compete with the main
   // k-blocks for the few pipeline stages.  YOLACT_B200_RESMMA=0 / 1 forces it off / on.
-  bool res_mma = a.ntaps * a.Cin_pad <= 128;
+  // In the pair form the half weight slice of a K = 256 expand (64 KB) stays resident next to 7 slab stages, so there the residual
+  // slabs ride the pipeline for free: 256->1024 @35 + residual 87 -> 73 us.
+  bool res_mma = ktot <= 128 || (pl->pair && ktot <= 256);
   if (const char* e = getenv("YOLACT_B200_RESMMA")) res_mma = atoi(e) != 0;
   pl->res_kb = (pl->tma_epi && a.residual && pl->BN % 64 == 0 && res_mma) ? pl->BN / 64 : 0;
   pl->nres = (pl->tma_epi && a.residual && !pl->res_kb) ? 2 : 0;   // residual buffers per epilogue group
