@@ -45,5 +45,5 @@ def full(path, out, title):
 if __name__ == '__main__':
     launch_list('gpurun_out/r1_launches.csv', 'profiles/r1_ncu_launch_list_bench.txt')
     full('gpurun_out/r1_prof_conv_tc.ncu-rep', 'profiles/r1_ncu_conv_tc_bench.txt',
-         'k_conv_tc inside bench.py: launches 28..33 of the timed steps = two layer3 bottlenecks (1x1 1024->256 [pair], 3x3 256->256 [pair+slab], 1x1 256->1024 +residual)')
+         'k_conv_tc inside bench.py: launches 28..33 of the timed steps = two layer3 bottlenecks (1x1 1024->256 [pair], 3x3 256->256 [pair+slab], 1x1 256->1024 +residual [pair + residual-MMA])')
     full('gpurun_out/r1_prof_post.ncu-rep', 'profiles/r1_ncu_postprocess_bench.txt', 'post-process kernels inside bench.py (res101@550 network output, B=64)')
