@@ -143,19 +143,22 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
 // completion of all prior MMAs of the pair -> the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3), "r"(issue)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -170,16 +173,29 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// The MMA warp runs its loops with all 32 lanes (warp-uniform control flow and operands, so descriptors and addresses stay
+// in uniform registers); only the tcgen05 instructions themselves are predicated on the one elected lane (`issue`).  Issued from
+// inside an `if (lane == 0)` region instead, every MMA costs an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence of ~15 dependent
+// instructions -- ~130 cycles, which bounds the N = 64 / 128 tiles (32 / 64 tensor cycles per MMA).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(issue)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -472,7 +488,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp == 1) {
     // ================= MMA issuer (pair: the leader CTA issues M=256 MMAs over both CTAs' operands) =================
-    if (lane == 0 && (!PAIR || rank == 0)) {
+    if (!PAIR || rank == 0) {
+      const uint32_t issue = elect_one();
       // instruction descriptor: D=f32, A=B=bf16 (1) or f16 (0), K-major both, N=BN, M=128
       const uint32_t fmt = F16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
@@ -499,15 +516,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const uint64_t db = umma_desc(smem_u32(sB + (size_t)(p.b_resident ? (3 * dy + dx) * p.kb_per_tap + kb : stage) * b_stage));
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
-                  if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
-                  else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+                  if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u, issue);
+                  else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u, issue);
                 }
                 if (!p.b_resident) {
-                  if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+                  if (PAIR) umma_commit_pair(&empty[stage], issue); else umma_commit(&empty[stage], issue);
                   if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
               }
-              if (PAIR) umma_commit_pair(&empty_a[sa]); else umma_commit(&empty_a[sa]);   // slab consumed by all three taps
+              if (PAIR) umma_commit_pair(&empty_a[sa], issue); else umma_commit(&empty_a[sa], issue);   // slab consumed by all three taps
               if (++sa == p.stages_a) { sa = 0; phase_a ^= 1; }
             }
           }
@@ -520,10 +537,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u, issue);
+            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u, issue);
           }
-          if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);   // smem stage free (in both CTAs) once these MMAs retire
+          if (PAIR) umma_commit_pair(&empty[stage], issue); else umma_commit(&empty[stage], issue);   // smem stage free (in both CTAs) once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         for (int j = 0; j < p.res_kb; ++j) {             // D[:, 64j .. 64j+63] += R_j x I
@@ -533,13 +550,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint64_t db = umma_desc(smem_u32(sEye));
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            if (PAIR) umma_pair(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u);
-            else umma_bf16(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u);
+            if (PAIR) umma_pair(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u, issue);
+            else umma_bf16(d_tmem + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_eye, 1u, issue);
           }
-          if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+          if (PAIR) umma_commit_pair(&empty[stage], issue); else umma_commit(&empty[stage], issue);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (PAIR) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);   // accumulator complete (each CTA holds its 128 rows)
+        if (PAIR) umma_commit_pair(&tmem_full[acc], issue); else umma_commit(&tmem_full[acc], issue);   // accumulator complete (each CTA holds its 128 rows)
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
