@@ -761,11 +761,8 @@ bool tc_overlapping_rows_ok() {
   return r == CUDA_SUCCESS;
 }
 
-static int pick_bn(int cout_pad, int ktot = 0) {
+static int pick_bn(int cout_pad) {
   if (const char* e = getenv("YOLACT_B200_BN")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0 && cout_pad % v == 0) return v; }   // tooling
-  // short-K convs (the 64->256 / 128->512 expands) are bound by the epilogue <-> MMA hand-off, not by operand traffic: half-width
-  // tiles pipeline twice as finely (64->256 @138: 259 -> 224 us, the HBM floor; 128->512 @69: 139 -> 121 us)
-  if (ktot > 0 && ktot <= 128 && cout_pad % 128 == 0) return 128;
   if (cout_pad % 256 == 0) return 256;
   for (int bn = 224; bn >= 64; bn -= 32)                               // largest 32-multiple divisor: 1152 -> 192, 288 -> 96
     if (cout_pad % bn == 0 && cout_pad > 256) return bn;
@@ -784,7 +781,7 @@ bool tc_supported(const ConvArgs& a) {
 int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   YB_REQUIRE(tc_supported(a), YB_ERR_UNSUPPORTED, "tc_plan_create: unsupported conv Cin=%d Cout_pad=%d", a.Cin, a.Cout_pad);
   TcPlan* pl = new TcPlan();
-  pl->BN = pick_bn(a.Cout_pad, a.ntaps * a.Cin_pad);
+  pl->BN = pick_bn(a.Cout_pad);
   int cols = 32;
   while (cols < 2 * pl->BN) cols <<= 1;
   pl->tmem_cols = cols;
