@@ -65,6 +65,8 @@ struct TcParams {
                           // it through descriptors that start 0 / 128 / 256 B into the slab (UMMA swizzles on absolute shared-memory
                           // address bits, so a row-shifted start needs no base offset: probed once, and every 3x3 parity test runs through it).  A third of the A
                           // traffic; the slab ring (stages_a slots of 17 KB) and the weight ring (stages) then advance separately.
+  int alt_tiles;          // narrow tiles (BN <= 64): the two epilogue groups take alternate TILES (group g owns accumulator g) instead of
+                          // alternate 32-column chunks of every tile, halving the per-tile hand-offs each warp sits through
   int res_kb;             // > 0: the residual is added BY THE TENSOR CORE: BN/64 extra k-blocks whose A tile is the
                           // residual's [128 x 64] slab and whose B tile is a shared-memory 64x64 identity (N=64 MMAs
                           // into the matching 64 accumulator columns) -- the epilogue never touches the residual
@@ -76,7 +78,7 @@ struct TcParams {
 
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb, pair, slab, stages_a;
+  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb, pair, slab, stages_a, alt_tiles;
   size_t smem_bytes;
 };
 
@@ -360,7 +362,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < 32; ++i) mbar_init(&res_full[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], PAIR ? 16 : 8); }   // pair: both CTAs' epilogue warps free the leader's accumulators
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (PAIR ? 16u : 8u) >> (p.alt_tiles ? 1 : 0)); }   // pair: both CTAs' epilogue warps free the leader's accumulators
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -574,7 +576,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     griddep_wait();
     const bool has_res = p.residual != nullptr && p.res_kb == 0;
     const int chunks_per_tile = (p.BN + 31) / 32;
-    const int my_chunks = (chunks_per_tile - grp + 1) / 2;            // chunks grp, grp+2, ...
+    const int cstep = p.alt_tiles ? 1 : 2, cfirst = p.alt_tiles ? 0 : grp;   // this warp's chunks: cfirst, cfirst + cstep, ...
+    const int my_chunks = p.alt_tiles ? chunks_per_tile : (chunks_per_tile - grp + 1) / 2;
     const int nres = p.nres;                                         // residual buffers per warp (power of two)
     const int nres_shift = nres == 4 ? 2 : (nres == 2 ? 1 : 0);
     uint8_t* gOut = sOut + wslot * (TC_OUT_BUFS * TC_WARP_TILE);
@@ -597,6 +600,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     int m_tile, n_tile;
     for (int it = 0; tile_at<PAIR>(p, it, m_tile, n_tile); ++it) {
+      if (p.alt_tiles && (it & 1) != grp) {                        // the other group's tile (accumulator acc == it & 1)
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       const long long m = (long long)m_tile * TC_BM + row_in_tile;
       const bool valid = m < p.M;
       int img = 0, y = 0, x = 0;
@@ -617,9 +624,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bool zero_row = halo || !valid;
         const int row0 = m_tile * TC_BM + quad * 32;
         uint32_t r[32];
-        if (my_chunks > 0) tmem_ld32(t_base + grp * 32, r);         // software pipeline: chunk j+1's TMEM load overlaps chunk j
+        if (my_chunks > 0) tmem_ld32(t_base + cfirst * 32, r);         // software pipeline: chunk j+1's TMEM load overlaps chunk j
         for (int j = 0; j < my_chunks; ++j, ++seq) {
-          const int c = 2 * j + grp;
+          const int c = cstep * j + cfirst;
           const int col = n0 + c * 32;
           const int obuf = seq & (TC_OUT_BUFS - 1);
           float v[32];
@@ -631,7 +638,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
-          if (j + 1 < my_chunks) tmem_ld32(t_base + (c + 2) * 32, r);
+          if (j + 1 < my_chunks) tmem_ld32(t_base + (c + cstep) * 32, r);
           if (has_res) {
             const int rbuf = seq & (nres - 1);
             mbar_wait(&gres_full[rbuf], (uint32_t)((seq >> nres_shift) & 1));
@@ -680,7 +687,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       } else {
         // direct-store path (dense fp32 outputs / odd tile widths): group g takes chunks c == g (mod 2)
-        for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
+        for (int c0 = cfirst * 32; c0 < p.BN; c0 += 32 * cstep) {
           uint32_t r[32];
           if (c0 + 32 <= p.BN) {
             tmem_ld32(t_base + c0, r);
@@ -810,6 +817,7 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   if (pl->nres) if (const char* e = getenv("YOLACT_B200_NRES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) pl->nres = v; }
   size_t epi_bytes = pl->tma_epi ? (size_t)8 * (TC_OUT_BUFS + pl->nres) * TC_WARP_TILE : 0;
   if (pl->res_kb) epi_bytes += 8192;                               // identity operand tile
+  pl->alt_tiles = (pl->BN <= 64 && pl->nres == 0 && !getenv("YOLACT_B200_NO_ALT")) ? 1 : 0;
   // slab mode (3x3, stride 1: the three dx taps of a tap row are consecutive rows of the same matrix)
   pl->slab = (a.ntaps == 9 && !pl->res_kb && !getenv("YOLACT_B200_NO_SLAB")) ? 1 : 0;
   for (int dy = 0; dy < 3 && pl->slab; ++dy)
@@ -884,7 +892,7 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
-  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a;
+  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a; p.alt_tiles = pl->alt_tiles;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
