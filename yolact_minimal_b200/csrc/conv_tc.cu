@@ -23,11 +23,12 @@
 //   slab      3x3 stride 1: one [130 x 64] A slab per (tap row, k-block) serves the three dx taps through
 //             row-shifted shared-memory descriptors; slab ring and weight ring advance separately
 //   res_kb    residual added by the tensor core: BN/64 extra k-blocks against an identity tile
+//   alt_tiles BN <= 64: the two epilogue groups take alternate tiles (one accumulator buffer each) instead of alternate chunks
 // Launches use programmatic dependent launch: everything before griddep_wait() touches only this
 // CTA's shared memory / TMEM (and the constant weights), so it overlaps the previous kernel's tail.
 //
 // Environment switches (tooling / A-B runs only): YOLACT_B200_PAIR=0|1, YOLACT_B200_RESMMA=0|1,
-// YOLACT_B200_NO_SLAB, YOLACT_B200_NO_BRES, YOLACT_B200_NO_PDL, YOLACT_B200_BN=<n>, YOLACT_B200_NRES=<n>.
+// YOLACT_B200_NO_SLAB, YOLACT_B200_NO_ALT, YOLACT_B200_NO_BRES, YOLACT_B200_NO_PDL, YOLACT_B200_BN=<n>, YOLACT_B200_NRES=<n>.
 #include "layers.cuh"
 
 #include <cuda.h>
