@@ -46,7 +46,6 @@ constexpr uint32_t TC_WARP_TILE = 32 * 32 * 2;  // 2 KiB: one warp's 32 rows x 3
 constexpr uint32_t TC_A_STAGE = TC_BM * TC_BK * 2;   // 16 KiB
 constexpr uint32_t TC_SLAB_ROWS = TC_BM + 2;         // slab mode: rows m0-1 .. m0+128 of one tap row
 constexpr uint32_t TC_A_SLAB = 136 * TC_BK * 2;      // 17 KiB slot: the 130-row slab padded to the 1 KiB swizzle period
-constexpr uint32_t TC_EPI_TILE = TC_BM * 32 * 2;     // 8 KiB: 128 rows x 32 columns of 16-bit outputs
 
 struct TcParams {
   long long M;            // rows to produce (B * plane)
@@ -79,7 +78,7 @@ struct TcParams {
 
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  int BN, stages, tmem_cols, tma_epi, nres, b_resident, grid_mult, res_kb, pair, slab, stages_a, alt_tiles;
+  int BN, stages, tmem_cols, tma_epi, nres, b_resident, res_kb, pair, slab, stages_a, alt_tiles;
   size_t smem_bytes;
 };
 
@@ -119,7 +118,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 // programmatic dependent launch: let the next grid's CTAs take over SMs as ours retire / block until the previous grid's
 // memory is complete and visible (both are no-ops for a launch without the programmatic-serialization attribute)
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -229,12 +227,6 @@ template <bool F16> __device__ __forceinline__ uint32_t pack2(float a, float b) 
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-}
-// no saturation (callers clamp when needed)
-template <bool F16> __device__ __forceinline__ uint32_t pack2_raw(float a, float b) {
-  if (F16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
 }
 // one F2FP per pair: round-to-nearest pack with the fp16 range clamp (and optionally ReLU) folded into the conversion
 template <bool F16, bool RELU> __device__ __forceinline__ uint32_t pack2_sat(float a, float b) {
@@ -828,11 +820,9 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   const size_t a_slot = pl->slab ? TC_A_SLAB : TC_A_STAGE;
   // weight-resident mode: the whole [BN x Ktot] slice fits next to >= 3 A stages
   pl->b_resident = 0;
-  pl->grid_mult = 1;
   const int n_tiles = a.Cout_pad / pl->BN;
   if (!getenv("YOLACT_B200_NO_BRES") && (size_t)num_kb * b_stage + epi_bytes + 3 * a_slot <= budget && n_tiles <= 64) {
     pl->b_resident = 1;
-    pl->grid_mult = n_tiles;
     int stages = (int)((budget - epi_bytes - (size_t)num_kb * b_stage) / a_slot);
     stages = stages > 8 ? 8 : stages;
     if (pl->slab) { pl->stages_a = stages; pl->stages = 1; } else pl->stages = stages;
