@@ -296,12 +296,35 @@ def gen_train(rcfg, ryolact):
     np.savez_compressed(os.path.join(HERE, 'train.npz'), **out)
 
 
+def gen_surface(rcfg, ryolact):
+    """Drop-in surface of the reference: state-dict layout (name, shape, dtype) of Yolact for every backbone in eval and
+    train mode, and the config attributes the hot path reads, per config name and mode."""
+    import contextlib, io, json, types
+    out = {'state_dict': {}, 'config': {}}
+    for arch in ('res50', 'res101', 'swin_tiny'):
+        for mode in ('detect', 'train'):
+            ns = types.SimpleNamespace(cfg=arch + '_coco', img_size=544, weight=None, traditional_nms=False, resume=None, train_bs=2,
+                                       val_interval=-1, val_num=-1, coco_api=False, visual_thre=0.0, save_lincomb=False, no_crop=False,
+                                       image=None, video=None, hide_mask=False, hide_bbox=False, hide_score=False, cutout=False,
+                                       real_time=False)
+            with contextlib.redirect_stdout(io.StringIO()):
+                cfg = rcfg.get_config(ns, mode)
+            net = ryolact.Yolact(cfg)
+            out['state_dict'][f'{arch}/{mode}'] = [[k, list(v.shape), str(v.dtype).replace('torch.', '')] for k, v in net.state_dict().items()]
+            keep = ('num_classes', 'aspect_ratios', 'img_size', 'scales', 'mode', 'nms_score_thre', 'nms_iou_thre', 'top_k', 'max_detections',
+                    'traditional_nms', 'pos_iou_thre', 'neg_iou_thre', 'masks_to_train', 'conf_alpha', 'bbox_alpha', 'mask_alpha',
+                    'semantic_alpha', 'visual_thre', 'lr', 'warmup_until', 'warmup_init', 'momentum', 'decay', 'bs_per_gpu')
+            out['config'][f'{arch}_coco/{mode}'] = {k: getattr(cfg, k) for k in keep if hasattr(cfg, k)}
+    json.dump(out, open(os.path.join(HERE, 'surface.json'), 'w'), indent=0, sort_keys=True)
+    print('  surface:', {k: len(v) for k, v in out['state_dict'].items()})
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     build_cython_nms()
     rcfg, ryolact, rout, rbox = import_reference()
-    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug', 'train']
+    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug', 'train', 'surface']
     if 'anchors' in which: gen_anchors(rcfg, ryolact)
     if 'hard' in which: gen_hard_nms()
     if 'post' in which: gen_postprocess(rcfg, rout)
@@ -309,4 +332,5 @@ if __name__ == '__main__':
     if 'forward' in which: gen_forward(rcfg, ryolact)
     if 'valaug' in which: gen_val_aug()
     if 'train' in which: gen_train(rcfg, ryolact)
+    if 'surface' in which: gen_surface(rcfg, ryolact)
     print('done')

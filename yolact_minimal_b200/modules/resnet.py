@@ -33,10 +33,10 @@ class ResNet(nn.Module):
     def __init__(self, layers):
         super().__init__()
         self.depth_blocks = tuple(layers)
+        self.layers = nn.ModuleList()           # registered before the stem, as in the reference (modules/resnet.py:49-55):
+        self.channels = []                      # state_dict() / parameters() enumerate in the same order
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
-        self.layers = nn.ModuleList()
-        self.channels = []
         inplanes = 64
         for stage, nblk in enumerate(layers):
             planes, stride = 64 * 2 ** stage, (1 if stage == 0 else 2)
