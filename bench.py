@@ -319,7 +319,7 @@ def run_ours(args):
         b2_.record(); torch.cuda.synchronize()
         with torch.no_grad():
             m2 = [o[:1].cpu().numpy() for o in net2(imgs[0][:1])]
-        other = {'dtype': 'bf16 operands, f32 accumulate', 'value_single_rank': BATCH * 10 / (a_.elapsed_time(b2_) / 1e3), 'steps': 10,
+        other = {'dtype': 'bf16', 'dtype_detail': 'bf16 operands, f32 accumulate', 'value_single_rank': BATCH * 10 / (a_.elapsed_time(b2_) / 1e3), 'steps': 10,
                  'parity_vs_fp32_oracle_max_abs_err': {n: float(np.abs(m - r).max()) for n, m, r in zip(('cls', 'box', 'coef', 'proto'), m2, ref)}}
         eng = net2.engine(BATCH)
 
@@ -351,7 +351,7 @@ def run_ours(args):
     cpu_v, cpu_s, cpu_nms_us = (0.0, 0.0, 0.0) if os.environ.get('YB_BENCH_SKIP_CPU') else cpu_reference_sample(4, 8, cores)
     line = {'metric': 'img/s', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision] + ' operands, f32 accumulate',
+            'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision], 'dtype_detail': 'tensor-core operands in that type, f32 accumulation; fp32 inputs and outputs',
             'data': 'synthetic',
             'config': {'workload': f'{ARCH}_coco {IMG}x{IMG} bs={BATCH}/GPU eval forward + decode/Fast-NMS/top-k (BASELINE.json configs[2] '
                                    f'at one GPU per {BATCH} images), random-init weights', 'global_batch': BATCH * world,
