@@ -296,7 +296,7 @@ def run_ours(args):
 
     # ---- the same step with bf16 operands (same kernels, same speed class; 8-bit mantissa) -----------------
     other = None
-    if args.precision == 'fp16' and not os.environ.get('YB_BENCH_SKIP_BF16'):
+    if args.precision == 'fp16' and world == 1 and not os.environ.get('YB_BENCH_SKIP_BF16'):
         del net, eng
         torch.cuda.empty_cache()
         cfg2 = make_config(ARCH + '_coco', IMG)
@@ -348,7 +348,8 @@ def run_ours(args):
                'frac': pp_bytes / (nms_us['stress'] * 1e-6) / 1e9 / pk['hbm'], 'alg_bytes_per_img': pp_bytes, 'regime': 'stress'}
 
     cores = host_cores()
-    cpu_v, cpu_s, cpu_nms_us = (0.0, 0.0, 0.0) if os.environ.get('YB_BENCH_SKIP_CPU') else cpu_reference_sample(4, 8, cores)
+    skip_cpu = world > 1 or os.environ.get('YB_BENCH_SKIP_CPU')           # the CPU baseline is a rank-0, N=1 measurement
+    cpu_v, cpu_s, cpu_nms_us = (0.0, 0.0, 0.0) if skip_cpu else cpu_reference_sample(4, 8, cores)
     line = {'metric': 'img/s', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision], 'dtype_detail': 'tensor-core operands in that type, f32 accumulation; fp32 inputs and outputs',
@@ -360,9 +361,9 @@ def run_ours(args):
             'tensor_frac_of_peak': value * GFLOP_PER_IMG * 1e9 / (world * pk['tf_sustained'] * 1e12),
             'gflop_per_img': GFLOP_PER_IMG,
             'fast_nms_us_per_img': nms_us, 'roofline': roofline, 'roofline_postprocess': pp_roof, 'kernel_breakdown': breakdown,
-            'cpu_baseline': {'value': cpu_v, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'8 reps x 4 images ({cpu_s:.1f} s): torch fp32 CPU forward + numpy nms()',
-                             'fast_nms_us_per_img': cpu_nms_us},
+            'cpu_baseline': None if skip_cpu else {'value': cpu_v, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
+                                                   'sample': f'8 reps x 4 images ({cpu_s:.1f} s): torch fp32 CPU forward + numpy nms()',
+                                                   'fast_nms_us_per_img': cpu_nms_us},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_fp32_oracle_max_abs_err': parity,
             'bf16_arm': other}
     print(json.dumps(line), flush=True)
