@@ -7,6 +7,8 @@ CPU restatement of the reference hot path (feiyuhuahuo/Yolact_minimal @ d920c05)
   * forward_torch.py  : plain-torch fp32 functional restatement of modules/yolact.py +
                         modules/resnet.py (floating-point kernel reference).
   * hard_nms.c        : plain-C restatement of cython_nms.pyx:24-74.
+  * train_np.py       : numpy restatement of the training targets and losses (match / encode, OHEM mining, the four
+                        losses, mask_iou), stage by stage -- the checker for native training kernels.
   * synth.py          : deterministic, library-independent synthetic input generator shared
                         by the golden generator and the tests.
 

@@ -296,6 +296,60 @@ def gen_train(rcfg, ryolact):
     np.savez_compressed(os.path.join(HERE, 'train.npz'), **out)
 
 
+def gen_train_stages(rcfg, ryolact, rbox):
+    """Stage-by-stage goldens of the training branch (oracle/train_np.py): the reference's match(), the OHEM selection
+    recovered from category_loss's internals, each of the four losses on synthetic head outputs, and mask_iou."""
+    import contextlib, io, types
+    from oracle import train_np as tn
+    out = {}
+    S, B = 128, 3
+    ns = types.SimpleNamespace(cfg='res50_coco', img_size=S, weight=None, traditional_nms=False, resume=None, train_bs=B,
+                               val_interval=-1, val_num=-1, coco_api=False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        cfg = rcfg.get_config(ns, 'train')
+    net = ryolact.Yolact(cfg)
+    anchors = torch.tensor(net.anchors).reshape(-1, 4)
+    A, P = anchors.shape[0], S // 4
+    tg, mk = synth.train_targets(9, B, S, n=4)
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    class_p = f32(synth.normal(21, 1, (B, A, cfg.num_classes)) * 2)
+    box_p = f32(synth.normal(21, 2, (B, A, 4)) * 0.5)
+    coef_p = torch.tanh(f32(synth.normal(21, 3, (B, A, 32))))
+    proto_p = torch.relu(f32(synth.normal(21, 4, (B, P, P, 32))))
+    seg_p = f32(synth.normal(21, 5, (B, cfg.num_classes - 1, S // 8, S // 8)))
+    offs, labs, mgt, midx = [], [], [], []
+    for i in range(B):
+        t = torch.from_numpy(tg[i])
+        o, c, g, m = rbox.match(cfg, t[:, :4], anchors, t[:, 4].long())
+        offs.append(o); labs.append(c); mgt.append(g); midx.append(m)
+    offs, labs, mgt, midx = torch.stack(offs), torch.stack(labs), torch.stack(mgt), torch.stack(midx)
+    pos = labs > 0
+    out['anchors'] = anchors.numpy(); out['offsets'] = offs.numpy(); out['labels'] = labs.numpy()
+    out['matched'] = mgt.numpy(); out['matched_idx'] = midx.numpy()
+    out['loss_c'] = np.float64(net.category_loss(class_p, labs, pos))
+    out['loss_b'] = np.float64(net.box_loss(box_p, offs, pos))
+    out['loss_m'] = np.float64(net.lincomb_mask_loss(pos, midx, coef_p, proto_p, [torch.from_numpy(m) for m in mk], mgt))
+    out['loss_s'] = np.float64(net.semantic_seg_loss(seg_p, [torch.from_numpy(m) for m in mk], [torch.from_numpy(t[:, 4]).long() for t in tg]))
+    # the OHEM negatives, recomputed exactly as category_loss does (modules/yolact.py:205-225)
+    bc = class_p.reshape(-1, cfg.num_classes); mx = bc.max()
+    mark = (torch.log(torch.sum(torch.exp(bc - mx), 1)) + mx - bc[:, 0]).reshape(B, -1)
+    mark[pos] = 0; mark[labs < 0] = 0
+    _, idx = mark.sort(1, descending=True); _, rank = idx.sort(1)
+    neg = rank < torch.clamp(3 * pos.long().sum(1, keepdim=True), max=A - 1)
+    neg[pos] = 0; neg[labs < 0] = 0
+    out['ohem_neg'] = neg.numpy()
+    m1 = torch.from_numpy((synth.uniform(31, 1, (5, 400)) > 0.5).astype(np.float32))
+    m2 = torch.from_numpy((synth.uniform(31, 2, (7, 400)) > 0.6).astype(np.float32))
+    out['mask_iou'] = rbox.mask_iou(m1, m2).numpy()
+    # the oracle must reproduce all of it before the fixture is written
+    o2, l2, g2, i2 = zip(*[tn.match(tg[i][:, :4], anchors.numpy(), tg[i][:, 4], cfg.pos_iou_thre, cfg.neg_iou_thre) for i in range(B)])
+    assert np.array_equal(np.stack(l2), out['labels']) and np.array_equal(np.stack(i2), out['matched_idx'])
+    assert np.allclose(np.stack(o2)[out['labels'] > 0], out['offsets'][out['labels'] > 0], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(tn.ohem_negatives(class_p.numpy(), out['labels']), out['ohem_neg'])
+    print('  train stages: pos', int(pos.sum()), 'neg', int(neg.sum()), 'losses', [round(float(out[k]), 5) for k in ('loss_c', 'loss_b', 'loss_m', 'loss_s')])
+    np.savez_compressed(os.path.join(HERE, 'train_stages.npz'), **out)
+
+
 def gen_surface(rcfg, ryolact):
     """Drop-in surface of the reference: state-dict layout (name, shape, dtype) of Yolact for every backbone in eval and
     train mode, and the config attributes the hot path reads, per config name and mode."""
@@ -324,7 +378,7 @@ if __name__ == '__main__':
     torch.set_num_threads(os.cpu_count())
     build_cython_nms()
     rcfg, ryolact, rout, rbox = import_reference()
-    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug', 'train', 'surface']
+    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug', 'train', 'surface', 'stages']
     if 'anchors' in which: gen_anchors(rcfg, ryolact)
     if 'hard' in which: gen_hard_nms()
     if 'post' in which: gen_postprocess(rcfg, rout)
@@ -333,4 +387,5 @@ if __name__ == '__main__':
     if 'valaug' in which: gen_val_aug()
     if 'train' in which: gen_train(rcfg, ryolact)
     if 'surface' in which: gen_surface(rcfg, ryolact)
+    if 'stages' in which: gen_train_stages(rcfg, ryolact, rbox)
     print('done')
