@@ -558,7 +558,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else {
     // ================= epilogue: 8 independent warps =================
     // Warp (grp, quad) owns rows quad*32..+31 (its TMEM lane quadrant) of the 32-column chunks
-    // c == grp (mod 2) of every tile, with private smem staging, mbarriers and bulk-async groups:
+    // c == grp (mod 2) of every tile (alt_tiles: all chunks of every other tile), with private smem staging, mbarriers and bulk-async groups:
     // TMEM -> registers -> (+bias, +residual tile prefetched by TMA, ReLU, halo) -> smem -> TMA store,
     // no block-level synchronisation anywhere in the epilogue.
     const int grp = (warp - 2) >> 2;
@@ -679,7 +679,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
       } else {
-        // direct-store path (dense fp32 outputs / odd tile widths): group g takes chunks c == g (mod 2)
+        // direct-store path (dense fp32 outputs / odd tile widths): same chunk assignment as above
         for (int c0 = cfirst * 32; c0 < p.BN; c0 += 32 * cstep) {
           uint32_t r[32];
           if (c0 + 32 <= p.BN) {
