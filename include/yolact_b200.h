@@ -152,6 +152,10 @@ YB_API int yb_net_proto_size(const yb_net* net);
 /* anchors [A,4] float32 (cx,cy,w,h), computed in float64 and rounded once (box_utils.py:86-101) */
 YB_API int yb_net_anchors_host(const yb_net* net, float* out);
 YB_API const float* yb_net_anchors_device(const yb_net* net);
+/* Replace the built-in anchor table (COCO scales int(S/544*{24,48,96,192,384}), ratios {1, 1/2, 2}: config.py:80-81) by the
+ * caller's [A,4] (cx,cy,w,h) float32 HOST table -- custom cfg.scales / cfg.aspect_ratios (e.g. res50_pascal, config.py:196).
+ * num_anchors must equal yb_net_num_anchors(); callable before or after finalize. */
+YB_API int yb_net_set_anchors(yb_net* net, const float* anchors_host, int num_anchors);
 
 /* img [B,3,S,S] NCHW float32 (device).  Outputs (device): cls [B,A,C] softmaxed, box [B,A,4],
  * coef [B,A,K] (tanh), proto [B,P,P,K] (relu, NHWC) -- Yolact.forward's eval 4-tuple. */

@@ -42,6 +42,14 @@ def _worker(rank, world, port, q):
     ydist.init_from_env(backend='gloo')
     det = _fake_det(4, 100, 32, 10 + rank)
     full = ydist.gather_detections(det)
+    # the product's own layout: typed views of ONE flat record (what the post-process kernels write), gathered asynchronously
+    from yolact_minimal_b200.utils.output_utils import record_views, record_numel
+    views = record_views(torch.empty(record_numel(4, 100, 32), dtype=torch.int32), 4, 100, 32)
+    for k, v in det.items():
+        views[k].copy_(v)
+    h = ydist.gather_detections(views, async_op=True)
+    again = h.wait().result()
+    assert all(torch.equal(full[k], again[k]) for k in full)
     q.put((rank, {k: v.numpy() for k, v in full.items()}))
     dist.barrier()
     dist.destroy_process_group()

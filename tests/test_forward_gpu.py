@@ -3,10 +3,11 @@
 Tolerances (absolute, on softmaxed class scores / box regressions / tanh coefficients / proto):
   fp32 mode  (CUDA cores)                       <= 1e-3 vs the fp32 oracle      (north_star)
   fp16 mode  (tcgen05, fp32 accumulate)         <= 1e-2 vs the fp32 oracle      (north_star's 16-bit bound)
-  bf16 mode  (tcgen05, fp32 accumulate)         <= 4e-2 vs the bf16-EMULATED oracle (the kernels compute
-             exactly the 16-bit pipeline), class scores <= 1e-2 (ResNet) and everything <= 5e-2 vs the fp32 oracle: an
-             8-bit-mantissa pipeline of ~100 layers cannot do better (oracle/forward_torch.forward_emulated
-             shows the same deviation on the CPU, independent of these kernels; DESIGN.md "precision")."""
+  bf16 mode  (tcgen05, fp32 accumulate)         NOT an inference parity mode: an 8-bit-mantissa pipeline of ~100 layers sits at
+             1-2e-2 from the fp32 oracle on box / coef / proto (oracle/forward_torch.forward_emulated shows the same deviation
+             on the CPU, independent of these kernels), so it makes no 1e-2 claim and has no bench arm.  The kernels themselves
+             are still pinned in that type (the training path computes in bf16): <= 4e-2 x scale vs the bf16-EMULATED oracle,
+             i.e. "the kernels compute exactly the 16-bit pipeline"."""
 import numpy as np
 import pytest
 import torch
@@ -16,7 +17,7 @@ from oracle import synth, forward_torch as ft, postprocess_np as pp
 
 pytestmark = pytest.mark.gpu
 
-TOL = {'fp32': 1e-3, 'fp16': 1e-2, 'bf16': 5e-2}
+TOL = {'fp32': 1e-3, 'fp16': 1e-2}
 
 
 def make_net(arch, S, precision, cuda, max_batch=0):
@@ -106,8 +107,8 @@ def test_forward_16bit_vs_oracle(cuda, arch, S, B, precision):
         err, err_emu = np.abs(m - r).max(), np.abs(m - e).max()
         print(f'{precision} {arch}@{S} {name}: max abs err vs fp32 oracle {err:.3e}, vs 16-bit emulation {err_emu:.3e} '
               f'(ref max {np.abs(r).max():.3f})')
-        tol = 1e-2 if (precision == 'fp16' or (name == 'cls' and arch != 'swin_tiny')) else TOL['bf16']
-        assert err < tol, (name, rel_err(m, r))
+        if precision == 'fp16':
+            assert err < TOL['fp16'], (name, rel_err(m, r))
         # same rounding points as the emulation: only summation order / 1-ulp flips remain
         assert err_emu < (4e-2 if precision == 'bf16' else 4e-3) * max(1.0, np.abs(r).max()), (name, rel_err(m, e))
 

@@ -32,3 +32,14 @@ def test_config_attributes_match_reference(name, mode):
         assert hasattr(cfg, k), k
         got = getattr(cfg, k)
         assert (list(got) if isinstance(got, (list, tuple)) else got) == v, (k, got, v)
+
+
+def test_default_precision_is_the_documented_one(monkeypatch):
+    """`Yolact(cfg)` as eval.py / detect.py construct it (no precision attribute) must run the mode every published number and
+    parity claim refers to: fp16 operands, fp32 accumulate."""
+    import inspect
+    from yolact_minimal_b200 import engine
+    monkeypatch.delenv('YOLACT_B200_PRECISION', raising=False)
+    assert engine.DEFAULT_PRECISION == 'fp16'
+    assert Yolact(make_config('res50_coco', 544)).precision == 'fp16'
+    assert inspect.signature(engine.Engine.sync).parameters['precision'].default == 'fp16'

@@ -57,6 +57,7 @@ PROTOTYPES = {
     'yb_net_proto_size': (C.c_int, [vp]),
     'yb_net_anchors_host': (C.c_int, [vp, vp]),
     'yb_net_anchors_device': (vp, [vp]),
+    'yb_net_set_anchors': (C.c_int, [vp, vp, C.c_int]),
     'yb_net_forward': (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     'yb_net_read_activation': (C.c_int, [vp, C.c_char_p, C.c_int, vp, C.c_int64, C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), vp]),

@@ -79,6 +79,7 @@ struct TcParams {
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
   int BN, stages, tmem_cols, tma_epi, nres, b_resident, res_kb, pair, slab, stages_a, alt_tiles;
+  int sms;                 // SM count of the device the plan was created on
   size_t smem_bytes;
 };
 
@@ -857,15 +858,25 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
     }
   }
   if (s != YB_OK) { delete pl; return s; }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) { delete pl; set_error("cudaFuncSetAttribute(k_conv_tc) failed: %s", cudaGetErrorString(attr_err)); return YB_ERR_CUDA; }
+  // function attributes are per device: opt every instantiation into 227 KB of dynamic shared memory on THIS device once
+  {
+    int dev = 0;
+    cudaError_t attr_err = cudaGetDevice(&dev);
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (attr_err == cudaSuccess && dev >= 0 && dev < 64 && !done[dev]) {
+      attr_err = cudaFuncSetAttribute(k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (attr_err == cudaSuccess) done[dev] = true;
+    }
+    if (attr_err != cudaSuccess) { delete pl; set_error("cudaFuncSetAttribute(k_conv_tc) failed: %s", cudaGetErrorString(attr_err)); return YB_ERR_CUDA; }
+  }
+  if (cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, [] { int d = 0; cudaGetDevice(&d); return d; }()) != cudaSuccess || pl->sms <= 0) {
+    delete pl; set_error("tc_plan_create: cannot read the SM count"); return YB_ERR_CUDA;
+  }
   *out = pl;
   return YB_OK;
 }
@@ -884,8 +895,7 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
   p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a; p.alt_tiles = pl->alt_tiles;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = pl->sms;
   const int total = p.m_tiles * p.n_tiles;
   const int max_units = pl->pair ? sms / 2 : sms;
   int units = total < max_units ? total : max_units;

@@ -634,6 +634,14 @@ extern "C" int yb_net_anchors_host(const yb_net* net, float* out) {
   return YB_OK;
 }
 
+extern "C" int yb_net_set_anchors(yb_net* net, const float* anchors_host, int num_anchors) {
+  YB_REQUIRE(net && anchors_host, YB_ERR_INVALID, "yb_net_set_anchors: NULL argument");
+  YB_REQUIRE(num_anchors == net->A, YB_ERR_INVALID, "yb_net_set_anchors: %d anchors, the network has %d", num_anchors, net->A);
+  net->anchors.assign(anchors_host, anchors_host + (size_t)net->A * 4);
+  if (net->d_anchors) YB_CHECK_CUDA(cudaMemcpy(net->d_anchors, net->anchors.data(), net->anchors.size() * 4, cudaMemcpyHostToDevice));
+  return YB_OK;
+}
+
 extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* cls, float* box, float* coef, float* proto,
                               void* stream_) {
   YB_REQUIRE(net && img && cls && box && coef && proto, YB_ERR_INVALID, "yb_net_forward: NULL argument");

@@ -58,14 +58,56 @@ def unpack_records(rec, max_det, coef_dim):
     return out
 
 
-def gather_detections(det, group=None):
-    """All-gather the detection records of every rank's shard (equal shard sizes).  Returns the
-    dict for the GLOBAL batch in rank order, on every rank."""
+class _Gather:
+    """Handle of an all-gather in flight: wait() orders the current stream after it, result() returns the global dict."""
+
+    def __init__(self, out, work, world, B, D, K):
+        self.out, self.work, self.dims = out, work, (world, B, D, K)
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        return self
+
+    def result(self):
+        self.wait()
+        world, B, D, K = self.dims
+        g, o, res = self.out, 0, {}
+        for name, n, shape, dt in (('count', B, (world * B,), torch.int32), ('cls', B * D, (world * B, D), torch.int32),
+                                   ('anchor', B * D, (world * B, D), torch.int32), ('score', B * D, (world * B, D), torch.float32),
+                                   ('box', B * D * 4, (world * B, D, 4), torch.float32), ('coef', B * D * K, (world * B, D, K), torch.float32)):
+            res[name] = g[:, o:o + n].contiguous().view(dt).view(shape)
+            o += n
+        return res
+
+
+def gather_detections(det, group=None, async_op=False):
+    """All-gather the detection records of every rank's shard (equal shard sizes) -- ONE NCCL call on the flat record that
+    output_utils.detect_batched's kernels wrote ('_flat'; dicts from elsewhere are packed first).  Returns the dict for the
+    GLOBAL batch in rank order, on every rank; with async_op=True a handle whose result() does, so that the collective overlaps
+    the next batch's forward (NCCL runs it on its own stream; wait()/result() order the current stream after it)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return det
+        return _Done(det) if async_op else det
     world = dist.get_world_size(group)
-    D, K = det['cls'].shape[1], det['coef'].shape[-1]
-    rec = pack_records(det)
-    out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
-    dist.all_gather_into_tensor(out, rec, group=group)
-    return unpack_records(out, D, K)
+    B, D = det['cls'].shape
+    K = det['coef'].shape[-1]
+    flat = det.get('_flat')
+    if flat is None:                                            # field-major per rank, as detect_batched lays it out
+        i32 = lambda t: t.contiguous().view(torch.int32).reshape(-1)
+        flat = torch.cat([i32(det['count']), i32(det['cls']), i32(det['anchor']), i32(det['score']), i32(det['box']), i32(det['coef'])])
+    out = torch.empty(world * flat.numel(), dtype=torch.int32, device=flat.device)
+    work = dist.all_gather_into_tensor(out, flat, group=group, async_op=True)
+    h = _Gather(out.view(world, flat.numel()), work, world, B, D, K)
+    return h if async_op else h.result()
+
+
+class _Done:
+    def __init__(self, det):
+        self.det = det
+
+    def wait(self):
+        return self
+
+    def result(self):
+        return self.det

@@ -10,6 +10,8 @@ import torch
 from . import _lib
 
 PRECISIONS = {'fp32': 0, 'bf16': 1, 'fp16': 2}
+# fp16 operands / fp32 accumulate: the 16-bit mode that meets north_star's 1e-2 bound
+DEFAULT_PRECISION = 'fp16'
 
 
 class Engine:
@@ -43,7 +45,7 @@ class Engine:
     def param_names(self):
         return [n for n, _ in self.names]
 
-    def sync(self, module, precision='bf16', min_batch=1):
+    def sync(self, module, precision=DEFAULT_PRECISION, min_batch=1):
         """(Re)load parameters when the module's tensors changed; (re)finalize when the batch
         grows or the precision changes."""
         if precision not in PRECISIONS:
@@ -63,6 +65,12 @@ class Engine:
             mb = max(min_batch, self.max_batch)
             _lib.check(self.L.yb_net_finalize(self.h, mb, PRECISIONS[precision]), 'yb_net_finalize')
         self._sig, self.max_batch, self.precision, self.device = sig, mb, precision, dev
+
+    def invalidate(self):
+        """Force the next forward to re-read every parameter.  sync() detects re-assigned or in-place
+        modified tensors through (_version, data_ptr); writes through `.data` (p.data.copy_(), EMA / weight
+        surgery) bump neither, so call this after them."""
+        self._sig = None
 
     def load_state(self, sd):
         for name, cnt in self.names:
@@ -121,6 +129,13 @@ class Engine:
         a = np.empty((self.num_anchors, 4), np.float32)
         _lib.check(self.L.yb_net_anchors_host(self.h, a.ctypes.data), 'yb_net_anchors_host')
         return a
+
+    def set_anchors(self, anchors):
+        """Use the caller's anchor table ([A,4] cx,cy,w,h) in the C pipelines (cfg.scales / cfg.aspect_ratios)."""
+        a = np.ascontiguousarray(np.asarray(anchors, dtype=np.float64).reshape(-1, 4).astype(np.float32))
+        if a.shape[0] != self.num_anchors:
+            raise ValueError(f'{a.shape[0]} anchors, the engine has {self.num_anchors}')
+        _lib.check(self.L.yb_net_set_anchors(self.h, a.ctypes.data, a.shape[0]), 'yb_net_set_anchors')
 
     def submit_host(self, img_host, params):
         """Pipelined end-to-end call (yb_net_submit_host): returns a ticket; the H2D copy of this batch

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from .resnet import ResNet, _no_forward
 from .swin_transformer import SwinTransformer
-from ..engine import Engine
+from ..engine import Engine, DEFAULT_PRECISION
 from ..utils.box_utils import all_anchors
 
 
@@ -90,7 +90,7 @@ class Yolact(nn.Module):
                 nn.init.xavier_uniform_(m.weight.data)
                 if m.bias is not None:
                     m.bias.data.zero_()
-        self.precision = getattr(cfg, 'precision', None) or os.environ.get('YOLACT_B200_PRECISION', 'bf16')
+        self.precision = getattr(cfg, 'precision', None) or os.environ.get('YOLACT_B200_PRECISION', DEFAULT_PRECISION)
         self.max_batch = int(getattr(cfg, 'max_batch', 0) or 0)
         self._engine = None
 
@@ -107,8 +107,16 @@ class Yolact(nn.Module):
     def engine(self, batch=1):
         if self._engine is None:
             self._engine = Engine(self.depth, self.cfg.img_size, self.cfg.num_classes, len(self.cfg.aspect_ratios), self.coef_dim)
+            a = self.anchors                                  # cfg.scales / cfg.aspect_ratios decide, not the engine's COCO defaults
+            self._engine.set_anchors(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a)
         self._engine.sync(self, precision=self.precision, min_batch=max(batch, self.max_batch))
         return self._engine
+
+    def refresh_engine(self):
+        """Call after modifying parameters through `.data` (EMA, weight surgery): those writes are invisible
+        to the engine's change detection (engine.Engine.invalidate)."""
+        if self._engine is not None:
+            self._engine.invalidate()
 
     def forward(self, img, box_classes=None, masks_gt=None):
         if self.training:

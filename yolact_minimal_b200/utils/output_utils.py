@@ -50,6 +50,21 @@ def _require_cuda(*tensors):
             raise _lib.YolactB200Error('yolact_minimal_b200 post-process needs CUDA tensors (no CPU fallback)')
 
 
+def record_numel(B, D, K):
+    return B * (1 + D * (7 + K))
+
+
+def record_views(flat, B, D, K):
+    """Typed views of a flat int32 detection record (layout above) -> the detect_batched dict; '_flat' is the buffer itself."""
+    o, out = 0, {'_flat': flat}
+    for name, n, shape, dt in (('count', B, (B,), torch.int32), ('cls', B * D, (B, D), torch.int32), ('anchor', B * D, (B, D), torch.int32),
+                               ('score', B * D, (B, D), torch.float32), ('box', B * D * 4, (B, D, 4), torch.float32),
+                               ('coef', B * D * K, (B, D, K), torch.float32)):
+        out[name] = flat[o:o + n].view(dt).view(shape)
+        o += n
+    return out
+
+
 def detect_batched(class_pred, box_pred, coef_pred, anchors, cfg):
     """Batched decode + (Fast|traditional) NMS + top-k.
     class_pred [B,A,C] (post-softmax), box_pred [B,A,4], coef_pred [B,A,K].
@@ -70,12 +85,9 @@ def detect_batched(class_pred, box_pred, coef_pred, anchors, cfg):
     p = _params(cfg, C, K)
     D = p.max_det
     L = _lib.lib()
-    out = dict(count=torch.empty(B, dtype=torch.int32, device=dev),
-               cls=torch.empty(B, D, dtype=torch.int32, device=dev),
-               anchor=torch.empty(B, D, dtype=torch.int32, device=dev),
-               score=torch.empty(B, D, dtype=torch.float32, device=dev),
-               box=torch.empty(B, D, 4, dtype=torch.float32, device=dev),
-               coef=torch.empty(B, D, K, dtype=torch.float32, device=dev))
+    # ONE flat int32 buffer [count B | class B*D | anchor B*D | score B*D | box B*D*4 | coef B*D*K]; the dict entries are typed views
+    # of it, so the kernels write the record that dist.gather_detections all-gathers directly (no pack pass)
+    out = record_views(torch.empty(record_numel(B, D, K), dtype=torch.int32, device=dev), B, D, K)
     with torch.cuda.device(dev):
         nbytes = L.yb_detect_workspace_bytes(B, A, ctypes.byref(p))
         ws = _workspace(nbytes, dev)
