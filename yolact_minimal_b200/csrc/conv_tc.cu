@@ -34,6 +34,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 
 namespace yb {
@@ -70,6 +71,12 @@ struct TcParams {
   int res_kb;             // > 0: the residual is added BY THE TENSOR CORE: BN/64 extra k-blocks whose A tile is the
                           // residual's [128 x 64] slab and whose B tile is a shared-memory 64x64 identity (N=64 MMAs
                           // into the matching 64 accumulator columns) -- the epilogue never touches the residual
+  int gemm;               // plain GEMM over long K (weight gradients): out[M x taps*Nper] (+)= A[M x K] * B_tap[Nper x K]^T with both operands
+                          // K-major; N tile n -> tap n / gemm_ntile_tap, B rows (n % gemm_ntile_tap) * BN, B columns k + gemm_shift[tap]
+                          // (the conv tap as a COLUMN offset of the transposed activations; out-of-range columns read as zero)
+  int gemm_ntile_tap;     // N tiles per tap
+  int gemm_shift[16];     // per-tap column shift of the B operand
+  int accumulate;         // out_mode 2: out += result (shared weights: one launch per use)
   Geom g;
   const float* bias;
   const void* residual;
@@ -80,6 +87,7 @@ struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
   int BN, stages, tmem_cols, tma_epi, nres, b_resident, res_kb, pair, slab, stages_a, alt_tiles;
   int sms;                 // SM count of the device the plan was created on
+  int gemm;                // plain-GEMM plan (tc_plan_create_gemm)
   size_t smem_bytes;
 };
 
@@ -250,6 +258,17 @@ template <bool F16> __device__ __forceinline__ float2 unpack2(uint32_t u) {
 template <int NCOL, bool F16>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t* acc, long long m, int col, bool valid, bool halo,
                                                int img, int y, int x) {
+  if (!valid) return;
+  if (p.out_mode == 2) {                                           // plain fp32 row-major [M][Cout_pad], no bias / activation
+    float* o = (float*)p.out + m * p.Cout_pad + col;
+#pragma unroll
+    for (int i = 0; i < NCOL; i += 4) {
+      float4 r = make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]), __uint_as_float(acc[i + 3]));
+      if (p.accumulate) { const float4 q = *reinterpret_cast<const float4*>(o + i); r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
+      *reinterpret_cast<float4*>(o + i) = r;
+    }
+    return;
+  }
   float v[NCOL];
 #pragma unroll
   for (int i = 0; i < NCOL; i += 4) {
@@ -257,7 +276,6 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
     v[i] = __uint_as_float(acc[i]) + b.x; v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
     v[i + 2] = __uint_as_float(acc[i + 2]) + b.z; v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
   }
-  if (!valid) return;
   if (p.out_mode == 0) {
     uint16_t* o = (uint16_t*)p.out + m * p.Cout + col;
     if (halo) {
@@ -451,7 +469,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
       for (int i = 0; !p.slab && tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
-        const int m0 = m_tile * TC_BM, n0 = n_tile * p.BN;
+        const int m0 = m_tile * TC_BM;
+        int n0 = n_tile * p.BN, bcol0 = 0;
+        if (p.gemm) {                                              // B tile: rows of the tap's operand, columns shifted by the tap
+          const int tap = n_tile / p.gemm_ntile_tap;
+          n0 = (n_tile - tap * p.gemm_ntile_tap) * p.BN;
+          bcol0 = p.gemm_shift[tap];
+        }
         for (int t = 0; t < p.ntaps; ++t) {
           const int row = m0 + p.tap_shift[t];
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
@@ -464,7 +488,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else {
               mbar_expect_tx(&full[stage], tx);
               tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmA, kb * TC_BK, row, &full[stage]);
-              if (!p.b_resident) tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0, &full[stage]);
+              if (!p.b_resident) tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK + bcol0, n0, &full[stage]);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -602,7 +626,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool valid = m < p.M;
       int img = 0, y = 0, x = 0;
       bool halo = false;
-      if (valid) {
+      if (valid && p.out_mode != 2) {
         const int plane = p.g.plane();
         img = (int)(m / plane);
         const int pos = (int)(m - (long long)img * plane);
@@ -762,6 +786,8 @@ bool tc_overlapping_rows_ok() {
   return r == CUDA_SUCCESS;
 }
 
+static int tc_device_setup(int* sms);
+
 static int pick_bn(int cout_pad) {
   if (const char* e = getenv("YOLACT_B200_BN")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0 && cout_pad % v == 0) return v; }   // tooling
   if (cout_pad % 256 == 0) return 256;
@@ -858,30 +884,93 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
     }
   }
   if (s != YB_OK) { delete pl; return s; }
-  // function attributes are per device: opt every instantiation into 227 KB of dynamic shared memory on THIS device once
-  {
-    int dev = 0;
-    cudaError_t attr_err = cudaGetDevice(&dev);
-    static std::mutex mu;
-    static bool done[64] = {};
-    std::lock_guard<std::mutex> lock(mu);
-    if (attr_err == cudaSuccess && dev >= 0 && dev < 64 && !done[dev]) {
-      attr_err = cudaFuncSetAttribute(k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (attr_err == cudaSuccess) done[dev] = true;
-    }
-    if (attr_err != cudaSuccess) { delete pl; set_error("cudaFuncSetAttribute(k_conv_tc) failed: %s", cudaGetErrorString(attr_err)); return YB_ERR_CUDA; }
-  }
-  if (cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, [] { int d = 0; cudaGetDevice(&d); return d; }()) != cudaSuccess || pl->sms <= 0) {
-    delete pl; set_error("tc_plan_create: cannot read the SM count"); return YB_ERR_CUDA;
-  }
+  { const int st = tc_device_setup(&pl->sms); if (st != YB_OK) { delete pl; return st; } }
+  pl->gemm = 0;
   *out = pl;
   return YB_OK;
 }
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
+
+// per-device one-time setup shared by the conv and GEMM plans: 227 KB of dynamic shared memory for every instantiation
+static int tc_device_setup(int* sms) {
+  int dev = 0;
+  YB_CHECK_CUDA(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static bool done[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 64 && !done[dev]) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done[dev] = true;
+  }
+  YB_CHECK_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  YB_REQUIRE(*sms > 0, YB_ERR_CUDA, "cannot read the SM count");
+  return YB_OK;
+}
+
+// ---- plain GEMM over long K on the same kernel (weight gradients; see TcParams::gemm) ---------------------------
+int tc_plan_create_gemm(const GemmArgs& g, TcPlan** out) {
+  YB_REQUIRE(g.act_dt == DT_BF16 || g.act_dt == DT_F16, YB_ERR_UNSUPPORTED, "tc_plan_create_gemm: 16-bit operands only");
+  YB_REQUIRE(g.M >= 1 && g.K >= 1 && g.lda % 8 == 0 && g.ldb % 8 == 0 && g.ntaps >= 1 && g.ntaps <= 16, YB_ERR_INVALID,
+             "tc_plan_create_gemm: M=%d K=%d lda=%d ldb=%d ntaps=%d", g.M, g.K, g.lda, g.ldb, g.ntaps);
+  int bn = 0;
+  if (g.Nper % 256 == 0) bn = 256;
+  else if (g.Nper <= 256 && g.Nper % 16 == 0) bn = g.Nper;
+  else if (g.Nper % 128 == 0) bn = 128;
+  else if (g.Nper % 64 == 0) bn = 64;
+  YB_REQUIRE(bn != 0, YB_ERR_UNSUPPORTED, "tc_plan_create_gemm: N per tap = %d has no tile", g.Nper);
+  TcPlan* pl = new TcPlan();
+  pl->gemm = 1; pl->BN = bn;
+  int cols = 32;
+  while (cols < 2 * bn) cols <<= 1;
+  pl->tmem_cols = cols;
+  pl->tma_epi = 0; pl->nres = 0; pl->b_resident = 0; pl->res_kb = 0; pl->pair = 0; pl->slab = 0; pl->stages_a = 0;
+  pl->alt_tiles = bn <= 64 ? 1 : 0;
+  const size_t b_stage = (size_t)bn * TC_BK * 2, per_stage = TC_A_STAGE + b_stage;
+  const size_t budget = 227 * 1024 - 2048;
+  int stages = (int)(budget / per_stage);
+  pl->stages = stages > 8 ? 8 : stages;
+  pl->smem_bytes = (size_t)pl->stages * per_stage + 2048;
+  const bool f16 = g.act_dt == DT_F16;
+  int s = make_map(&pl->tmA, g.a, (uint64_t)g.K, (uint64_t)g.M, TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)g.lda);
+  if (s == YB_OK) s = make_map(&pl->tmB, g.b, (uint64_t)g.Kb, (uint64_t)g.Nper, (uint32_t)bn, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)g.ldb);
+  pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;
+  if (s == YB_OK) s = tc_device_setup(&pl->sms);
+  if (s != YB_OK) { delete pl; return s; }
+  *out = pl;
+  return YB_OK;
+}
+
+int launch_gemm_tc(const TcPlan* pl, const GemmArgs& g, cudaStream_t s) {
+  YB_REQUIRE(pl && pl->gemm, YB_ERR_INVALID, "launch_gemm_tc: not a GEMM plan");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M;
+  p.m_tiles = (g.M + TC_BM - 1) / TC_BM;
+  p.gemm = 1; p.gemm_ntile_tap = g.Nper / pl->BN;
+  p.n_tiles = g.ntaps * p.gemm_ntile_tap;
+  p.kb_per_tap = (g.K + TC_BK - 1) / TC_BK;
+  p.ntaps = 1; p.tap_shift[0] = 0;
+  for (int i = 0; i < g.ntaps; ++i) p.gemm_shift[i] = g.shift[i];
+  p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
+  p.Cout = p.Cout_pad = g.ntaps * g.Nper; p.relu = 0; p.out_mode = 2; p.accumulate = g.accumulate;
+  p.is_f16 = g.act_dt == DT_F16; p.alt_tiles = pl->alt_tiles;
+  p.g.H = 1 << 20; p.g.W = 1 << 20;
+  p.bias = nullptr; p.residual = nullptr; p.out = g.out;
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < pl->sms ? total : pl->sms;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = s;
+  cfg.attrs = nullptr; cfg.numAttrs = 0;
+  const cudaError_t le = p.is_f16 ? cudaLaunchKernelEx(&cfg, k_conv_tc<true, false>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p)
+                                  : cudaLaunchKernelEx(&cfg, k_conv_tc<false, false>, pl->tmA, pl->tmB, pl->tmOut, pl->tmRes, p);
+  YB_CHECK_CUDA(le);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
 
 int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   TcParams p;
@@ -895,6 +984,8 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
   p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a; p.alt_tiles = pl->alt_tiles;
+  p.gemm = 0; p.gemm_ntile_tap = 1; p.accumulate = 0;
+  for (int i = 0; i < 16; ++i) p.gemm_shift[i] = 0;
   const int sms = pl->sms;
   const int total = p.m_tiles * p.n_tiles;
   const int max_units = pl->pair ? sms / 2 : sms;

@@ -64,6 +64,17 @@ void tc_plan_destroy(TcPlan* p);
 int launch_conv_tc(const TcPlan* p, const ConvArgs& a, cudaStream_t s);
 bool tc_supported(const ConvArgs& a);
 
+// plain GEMM over a long K on the tcgen05 kernel (weight gradients):  out[M][ntaps*Nper] (+)= A[M][K] x B_tap[Nper][K]^T, fp32 out,
+// both operands 16-bit and K-major (row = output index, columns = K); tap t reads B at columns k + shift[t] (zero outside [0, Kb)).
+struct GemmArgs {
+  const void* a; const void* b; float* out;
+  int act_dt, M, Nper, K, lda, ldb, ntaps, accumulate;
+  long long Kb;            // addressable columns of b
+  int shift[16];
+};
+int tc_plan_create_gemm(const GemmArgs& g, TcPlan** out);
+int launch_gemm_tc(const TcPlan* p, const GemmArgs& g, cudaStream_t s);
+
 int launch_stem(const float* img_nchw, const float* w /*[7][7][3][64]*/, const float* bias, void* out, int out_dt,
                 int B, int S, int H1, cudaStream_t s);
 int launch_stem_s2d(const float* img_nchw, void* out /*[B][(H1+2)^2][16 | 64]*/, int dt, int wide, int B, int S, int H1, cudaStream_t s);

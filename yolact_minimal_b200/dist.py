@@ -73,12 +73,10 @@ class _Gather:
     def result(self):
         self.wait()
         world, B, D, K = self.dims
-        g, o, res = self.out, 0, {}
-        for name, n, shape, dt in (('count', B, (world * B,), torch.int32), ('cls', B * D, (world * B, D), torch.int32),
-                                   ('anchor', B * D, (world * B, D), torch.int32), ('score', B * D, (world * B, D), torch.float32),
-                                   ('box', B * D * 4, (world * B, D, 4), torch.float32), ('coef', B * D * K, (world * B, D, K), torch.float32)):
-            res[name] = g[:, o:o + n].contiguous().view(dt).view(shape)
-            o += n
+        from .utils.output_utils import record_fields
+        res = {}
+        for name, o, n, shape, dt in record_fields(B, D, K)[0]:
+            res[name] = self.out[:, o:o + n].contiguous().view(dt).view((world * shape[0],) + tuple(shape[1:]))
         return res
 
 
@@ -94,8 +92,11 @@ def gather_detections(det, group=None, async_op=False):
     K = det['coef'].shape[-1]
     flat = det.get('_flat')
     if flat is None:                                            # field-major per rank, as detect_batched lays it out
-        i32 = lambda t: t.contiguous().view(torch.int32).reshape(-1)
-        flat = torch.cat([i32(det['count']), i32(det['cls']), i32(det['anchor']), i32(det['score']), i32(det['box']), i32(det['coef'])])
+        from .utils.output_utils import record_views, record_numel
+        v = record_views(torch.zeros(record_numel(B, D, K), dtype=torch.int32, device=det['cls'].device), B, D, K)
+        for k in ('count', 'cls', 'anchor', 'score', 'box', 'coef'):
+            v[k].copy_(det[k])
+        flat = v['_flat']
     out = torch.empty(world * flat.numel(), dtype=torch.int32, device=flat.device)
     work = dist.all_gather_into_tensor(out, flat, group=group, async_op=True)
     h = _Gather(out.view(world, flat.numel()), work, world, B, D, K)

@@ -50,18 +50,27 @@ def _require_cuda(*tensors):
             raise _lib.YolactB200Error('yolact_minimal_b200 post-process needs CUDA tensors (no CPU fallback)')
 
 
-def record_numel(B, D, K):
-    return B * (1 + D * (7 + K))
-
-
-def record_views(flat, B, D, K):
-    """Typed views of a flat int32 detection record (layout above) -> the detect_batched dict; '_flat' is the buffer itself."""
-    o, out = 0, {'_flat': flat}
+def record_fields(B, D, K):
+    """(name, int32 offset, element count, shape, dtype) of every field of the flat detection record.  Field offsets are
+    16-byte aligned: the post-process kernels store boxes / coefficients with 128-bit vector writes."""
+    fields, o = [], 0
     for name, n, shape, dt in (('count', B, (B,), torch.int32), ('cls', B * D, (B, D), torch.int32), ('anchor', B * D, (B, D), torch.int32),
                                ('score', B * D, (B, D), torch.float32), ('box', B * D * 4, (B, D, 4), torch.float32),
                                ('coef', B * D * K, (B, D, K), torch.float32)):
+        fields.append((name, o, n, shape, dt))
+        o += (n + 3) // 4 * 4
+    return fields, o
+
+
+def record_numel(B, D, K):
+    return record_fields(B, D, K)[1]
+
+
+def record_views(flat, B, D, K):
+    """Typed views of a flat int32 detection record -> the detect_batched dict; '_flat' is the buffer itself."""
+    out = {'_flat': flat}
+    for name, o, n, shape, dt in record_fields(B, D, K)[0]:
         out[name] = flat[o:o + n].view(dt).view(shape)
-        o += n
     return out
 
 
