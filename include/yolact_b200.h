@@ -209,6 +209,68 @@ YB_API int yb_net_submit_host(yb_net* net, const float* img_host, int batch, con
 YB_API int yb_net_collect_host(yb_net* net, int ticket, int32_t* out_count, int32_t* out_class, int32_t* out_anchor,
                                float* out_score, float* out_box, float* out_coef);
 
+/* ------------------------------------------------------------------------------------------
+ * Training targets, losses and their gradients, batched -- replaces Yolact.compute_loss and the four loss functions
+ * (modules/yolact.py:166-313) with utils/box_utils.py:57-114 match() / encode() and :147-168 crop().
+ *   cls [B,A,C] RAW class logits, box [B,A,4], coef [B,A,K] (tanh applied), proto [B,P,P,K] (relu applied, NHWC),
+ *   seg [B,Hs,Hs,ld_seg] segmentation logits, NHWC with row stride ld_seg >= C-1 (the reference's tensor is NCHW),
+ *   anchors [A,4] (cx,cy,w,h), gt [total_gt,5] = (x1,y1,x2,y2 in [0,1], 0-based label) of all images back to back,
+ *   gt_offset [B+1] int32 (image b owns rows gt_offset[b] .. gt_offset[b+1]), gt_masks [total_gt,S,S] float 0/1.
+ * All pointers are DEVICE pointers except p (grad_scale: 4 DEVICE floats, NULL = ones).  losses[4] = (category, box, mask, semantic), weighted by
+ * the *_alpha fields as the reference returns them.  The gradient outputs are optional (all NULL = losses only); they are the
+ * derivatives of  sum_i grad_scale[i] * losses[i]  w.r.t. cls / box / coef (the tanh OUTPUT) / proto (the relu OUTPUT) / seg.
+ * More than masks_to_train positives in an image: a uniformly random subset (counter-based hash of `seed`; the reference
+ * draws torch.randperm, yolact.py:261-268).  dbg_* (optional): labels (>0 fg class+1, 0 bg, -1 neutral), matched gt index,
+ * SSD offsets, mined-negative flags -- what match() / the OHEM step of the reference produce, for the parity tests.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int batch, num_anchors, num_classes /* incl. background */, coef_dim, proto_size, seg_size, mask_size;
+  float pos_iou_thr, neg_iou_thr;        /* cfg.pos_iou_thre / neg_iou_thre (config.py:103-104) */
+  int neg_pos_ratio, masks_to_train;     /* 3 (yolact.py:205), cfg.masks_to_train (config.py:112) */
+  float conf_alpha, bbox_alpha, mask_alpha, semantic_alpha;   /* config.py:106-109 */
+} yb_loss_params;
+
+YB_API size_t yb_losses_workspace_bytes(const yb_loss_params* p, int total_gt);
+YB_API int yb_losses(const yb_loss_params* p, const float* cls, const float* box, const float* coef, const float* proto, const float* seg, int ld_seg,
+                     const float* anchors, const float* gt, const int32_t* gt_offset, const float* gt_masks, int total_gt, int max_gt_per_image,
+                     uint32_t seed, const float* grad_scale, float* losses, float* d_cls, float* d_box, float* d_coef, float* d_proto, float* d_seg,
+                     int32_t* dbg_labels, int32_t* dbg_matched_idx, float* dbg_offsets, uint8_t* dbg_neg, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training engine: Yolact.forward in training mode (modules/yolact.py:141-161) and its backward pass, ResNet-50/101 backbones.
+ * Train-mode forward = tcgen05 convolutions on 16-bit activations + batch-statistics BatchNorm (running statistics updated in
+ * place, momentum 0.1) + the loss kernels above; backward = dgrad convolutions and weight-gradient GEMMs on the same tcgen05
+ * kernel, BatchNorm / pooling / up-sampling backward on CUDA cores.  The fp32 master parameters stay where the caller keeps
+ * them (torch nn.Parameters): yb_train_bind hands over DEVICE pointers to each parameter / buffer and to the fp32 buffer that
+ * receives its gradient; nothing is copied, optimizers and DDP see one set of tensors.
+ *   create -> param_info / bind (all) -> [forward -> backward]*
+ * ---------------------------------------------------------------------------------------- */
+typedef struct yb_train yb_train;
+typedef struct {
+  float pos_iou_thr, neg_iou_thr;
+  int neg_pos_ratio, masks_to_train;
+  float conf_alpha, bbox_alpha, mask_alpha, semantic_alpha;
+  float bn_momentum, bn_eps;             /* torch defaults 0.1 / 1e-5 */
+} yb_train_hparams;
+
+/* precision: YB_PREC_BF16 (recommended: gradients need the exponent range) or YB_PREC_FP16 */
+YB_API int yb_train_create(const yb_net_config* cfg, int batch, int precision, yb_train** out);
+YB_API void yb_train_destroy(yb_train* t);
+/* bindable tensors: kind 0 = parameter (data + gradient buffer), 1 = buffer (running_mean / running_var; no gradient) */
+YB_API int yb_train_num_tensors(const yb_train* t);
+YB_API int yb_train_tensor_info(const yb_train* t, int i, const char** name, int64_t* count, int* kind);
+YB_API int yb_train_bind(yb_train* t, const char* name, float* data_device, float* grad_device);
+YB_API int yb_train_set_anchors(yb_train* t, const float* anchors_host, int num_anchors);
+/* img [B,3,S,S] float32 NCHW; gt / gt_offset / gt_masks as in yb_losses; losses[4] (device).  Asynchronous on `stream`. */
+YB_API int yb_train_forward(yb_train* t, const float* img, const float* gt, const int32_t* gt_offset, const float* gt_masks, int total_gt,
+                            int max_gt_per_image, const yb_train_hparams* hp, uint32_t seed, float* losses, void* stream);
+/* gradients of sum_i loss_grad[i] * losses[i] (loss_grad: 4 DEVICE floats, NULL = ones) into the bound gradient buffers (overwritten) */
+YB_API int yb_train_backward(yb_train* t, const float* loss_grad, void* stream);
+/* debug / parity taps: copy a named activation (grad = 0) or its gradient (grad = 1) as NCHW float32 [B,C,H,H] (device) */
+YB_API int yb_train_read(yb_train* t, const char* name, int grad, float* out, int64_t out_count, int* C, int* H, void* stream);
+YB_API uint64_t yb_train_launches_per_step(const yb_train* t);
+
 #ifdef __cplusplus
 }
 #endif

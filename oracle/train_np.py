@@ -1,8 +1,7 @@
 """oracle/train_np.py -- TEST INFRASTRUCTURE (see oracle/__init__.py).
 
 numpy fp32 restatement of the reference's training targets and losses, function by function, so that
-native kernels for SURVEY.md 8 row a12 / f3 can be checked stage by stage (today the product runs this
-branch on torch autograd, yolact_minimal_b200/train_torch.py):
+the native kernels for SURVEY.md 8 row a12 / f3 (yolact_minimal_b200/csrc/losses.cu) can be checked stage by stage:
 
   match            utils/box_utils.py:57-83    per image: IoU[gt, anchor] -> best gt per anchor, each gt claims
                                                its best anchor (IoU := 2, later gt wins a shared anchor),

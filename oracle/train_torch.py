@@ -1,12 +1,10 @@
-"""Training branch of `Yolact.forward` (reference: modules/yolact.py:159-161,:166-313 and
-utils/box_utils.py:57-114) -- FIRST CUT on ATen/cuDNN, exactly as SURVEY.md section 7 step 7 plans it.
+"""oracle/train_torch.py -- TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-This is NOT the B200-native product path: the eval forward and the whole post-process run on the
-hand-written kernels behind libyolact_b200.so; training needs batch-statistics BatchNorm and a
-backward pass, which this round delegates to torch autograd so that the reference's train.py
-(DDP over NCCL, SGD, warm-up, checkpoints) keeps working against this package with identical
-numerics.  It uses the SAME nn.Conv2d / nn.BatchNorm2d leaf modules that hold the weights for the
-engine, so DDP hooks, optimizers and state dicts see one set of parameters.  ResNet backbones only.
+torch-autograd restatement of the reference's training branch (modules/yolact.py:159-161,:166-313 and
+utils/box_utils.py:57-114): train-mode forward on ATen ops over the product's parameter-container modules, target
+assignment and the four losses.  Round 1 shipped this file as the product's training path; round 2 replaced it with the native
+engine (yolact_minimal_b200/csrc/train.cu, losses.cu) and keeps it here as the fp32 CHECKER that the native losses,
+activations and parameter gradients are compared against (tests/test_train_gpu.py).  ResNet backbones only.
 """
 import torch
 import torch.nn.functional as F
@@ -23,18 +21,26 @@ def _bottleneck(blk, x):
     return F.relu(out + res)
 
 
-def forward_train(net, img):
+def forward_train(net, img, taps=None):
+    """taps: optional dict that receives named intermediate activations (the native engine's tensor names), each with
+    retain_grad() so that their gradients can be compared after backward."""
+    def tap(name, t):
+        if taps is not None:
+            if t.requires_grad:
+                t.retain_grad()
+            taps[name] = t
+        return t
     bb = net.backbone
     if not hasattr(bb, 'conv1'):
         raise NotImplementedError('training forward is implemented for the ResNet backbones only')
-    x = F.max_pool2d(F.relu(bb.bn1(bb.conv1(img))), kernel_size=3, stride=2, padding=1)
+    x = tap('pool', F.max_pool2d(tap('stem.z', F.relu(bb.bn1(tap('stem.y', bb.conv1(img))))), kernel_size=3, stride=2, padding=1))
     feats = []
     for stage in bb.layers:
         for i, blk in enumerate(stage):
             if i > 0 and blk.downsample is not None:            # container quirk: only block 0 owns the shortcut
                 raise RuntimeError('unexpected downsample')
             x = _bottleneck(blk, x)
-        feats.append(x)
+        feats.append(tap('c%d' % (len(feats) + 2), x))
     c3, c4, c5 = feats[1:]
     fpn = net.fpn
     up = lambda t, like: F.interpolate(t, size=like.shape[2:], mode='bilinear', align_corners=False)
@@ -43,13 +49,14 @@ def forward_train(net, img):
     p4_1 = l4 + up(p5_1, l4)
     l3 = fpn.lat_layers[0](c3)
     p3_1 = l3 + up(p4_1, l3)
-    p5, p4, p3 = fpn.pred_layers[2](p5_1), fpn.pred_layers[1](p4_1), fpn.pred_layers[0](p3_1)
-    p6 = fpn.downsample_layers[0](p5)
-    p7 = fpn.downsample_layers[1](p6)
+    tap('p5_1', p5_1); tap('p4_1', p4_1); tap('p3_1', p3_1)
+    p5, p4, p3 = tap('p5', fpn.pred_layers[2](p5_1)), tap('p4', fpn.pred_layers[1](p4_1)), tap('p3', fpn.pred_layers[0](p3_1))
+    p6 = tap('p6', fpn.downsample_layers[0](p5))
+    p7 = tap('p7', fpn.downsample_layers[1](p6))
     levels = (p3, p4, p5, p6, p7)
 
     pn = net.proto_net
-    proto = pn.proto2(F.interpolate(pn.proto1(p3), scale_factor=2, mode='bilinear', align_corners=True))
+    proto = pn.proto2(tap('proto.up', F.interpolate(tap('proto1.4', pn.proto1(p3)), scale_factor=2, mode='bilinear', align_corners=True)))
     proto = proto.permute(0, 2, 3, 1).contiguous()
 
     pl, B = net.prediction_layers, img.shape[0]
@@ -201,7 +208,7 @@ def compute_loss(net, class_p, box_p, coef_p, proto_p, seg_p, box_classes, masks
             mask_loss(cfg, pos, best_gt, coef_p, proto_p, masks_gt, matched), semantic_loss(cfg, seg_p, masks_gt, class_gt))
 
 
-def training_step_forward(net, img, box_classes, masks_gt):
+def training_step_forward(net, img, box_classes, masks_gt, taps=None):
     """Yolact.forward in training mode: the reference's 4-tuple of losses."""
-    outs = forward_train(net, img)
+    outs = forward_train(net, img, taps)
     return compute_loss(net, *outs, box_classes, masks_gt)

@@ -1,7 +1,8 @@
 """CPU: the training branch stage by stage.  tests/golden/train_stages.npz holds what the reference's match(), OHEM mining,
 four loss functions and mask_iou return on synthetic head outputs (tests/golden/make_golden.py stages); checked here are
 (1) the numpy oracle oracle/train_np.py -- the checker native training kernels will be held to -- and
-(2) the product's current torch implementation (yolact_minimal_b200/train_torch.py), function by function."""
+(2) the torch-autograd checker oracle/train_torch.py, function by function (the native kernels are held to both on the GPU:
+tests/test_train_gpu.py)."""
 import numpy as np
 import torch
 
@@ -41,8 +42,8 @@ def test_oracle_matches_reference_stage_by_stage():
     assert np.allclose(tn.mask_iou(m1, m2), g['mask_iou'], rtol=1e-6)
 
 
-def test_product_torch_training_functions_match_reference():
-    from yolact_minimal_b200 import train_torch as tt
+def test_torch_checker_training_functions_match_reference():
+    from oracle import train_torch as tt
     from yolact_minimal_b200.config import make_config
     g = load_golden('train_stages.npz')
     tg, mk, class_p, box_p, coef_p, proto_p, seg_p = inputs(g)

@@ -30,6 +30,19 @@ class NetConfig(C.Structure):
                 ('coef_dim', C.c_int)]
 
 
+class LossParams(C.Structure):
+    _fields_ = [('batch', C.c_int), ('num_anchors', C.c_int), ('num_classes', C.c_int), ('coef_dim', C.c_int), ('proto_size', C.c_int),
+                ('seg_size', C.c_int), ('mask_size', C.c_int), ('pos_iou_thr', C.c_float), ('neg_iou_thr', C.c_float),
+                ('neg_pos_ratio', C.c_int), ('masks_to_train', C.c_int), ('conf_alpha', C.c_float), ('bbox_alpha', C.c_float),
+                ('mask_alpha', C.c_float), ('semantic_alpha', C.c_float)]
+
+
+class TrainHparams(C.Structure):
+    _fields_ = [('pos_iou_thr', C.c_float), ('neg_iou_thr', C.c_float), ('neg_pos_ratio', C.c_int), ('masks_to_train', C.c_int),
+                ('conf_alpha', C.c_float), ('bbox_alpha', C.c_float), ('mask_alpha', C.c_float), ('semantic_alpha', C.c_float),
+                ('bn_momentum', C.c_float), ('bn_eps', C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/yolact_b200.h
 PROTOTYPES = {
     'yb_version': (C.c_int, []),
@@ -68,6 +81,19 @@ PROTOTYPES = {
     'yb_net_last_proto': (vp, [vp]),
     'yb_net_submit_host': (C.c_int, [vp, vp, C.c_int, C.POINTER(DetectParams), C.POINTER(C.c_int)]),
     'yb_net_collect_host': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp]),
+    'yb_losses_workspace_bytes': (C.c_size_t, [C.POINTER(LossParams), C.c_int]),
+    'yb_losses': (C.c_int, [C.POINTER(LossParams), vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_uint32, vp, vp,
+                            vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    'yb_train_create': (C.c_int, [C.POINTER(NetConfig), C.c_int, C.c_int, C.POINTER(vp)]),
+    'yb_train_destroy': (None, [vp]),
+    'yb_train_num_tensors': (C.c_int, [vp]),
+    'yb_train_tensor_info': (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    'yb_train_bind': (C.c_int, [vp, C.c_char_p, vp, vp]),
+    'yb_train_set_anchors': (C.c_int, [vp, vp, C.c_int]),
+    'yb_train_forward': (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(TrainHparams), C.c_uint32, vp, vp]),
+    'yb_train_backward': (C.c_int, [vp, vp, vp]),
+    'yb_train_read': (C.c_int, [vp, C.c_char_p, C.c_int, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), vp]),
+    'yb_train_launches_per_step': (C.c_uint64, [vp]),
 }
 
 _lib = None

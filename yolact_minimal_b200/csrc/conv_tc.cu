@@ -873,7 +873,8 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
   int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, pl->slab ? TC_SLAB_ROWS : TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.in_row_stride);
-  if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN), f16);
+  if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN), f16, TC_BK,
+                               CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.w_ld);
   pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;                      // placeholders when the TMA epilogue is off
   if (s == YB_OK && pl->tma_epi) {
     const uint64_t out_rows = (uint64_t)max_batch * a.g.plane();

@@ -3,62 +3,11 @@
 // split for stride-2 convs, FPN upsample+add, protonet upsample, head softmax/tanh scatter).
 // All activations use the haloed NHWC layout described in layers.cuh.
 #include "layers.cuh"
+#include "vecio.cuh"
 #include <math.h>
 #include <algorithm>
 
 namespace yb {
-
-template <typename T> struct Act;
-template <> struct Act<float> {
-  static __device__ __forceinline__ float ld(const float* p) { return *p; }
-  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
-};
-template <> struct Act<__half> {
-  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
-  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
-};
-template <> struct Act<__nv_bfloat16> {
-  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-};
-
-// 16-byte vector of activations: 4 floats or 8 halfs/bf16s
-template <typename T> struct VecIO;
-template <> struct VecIO<float> {
-  static constexpr int N = 4;
-  static __device__ __forceinline__ void load(const float* p, float* f) { const float4 v = *reinterpret_cast<const float4*>(p); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
-  static __device__ __forceinline__ void store(float* p, const float* f) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
-};
-template <> struct VecIO<__half> {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ void load(const __half* p, float* f) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-  }
-  static __device__ __forceinline__ void store(__half* p, const float* f) {
-    uint4 v; __half2* h = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(fminf(fmaxf(f[2 * i], -65504.f), 65504.f), fminf(fmaxf(f[2 * i + 1], -65504.f), 65504.f));
-    *reinterpret_cast<uint4*>(p) = v;
-  }
-};
-template <> struct VecIO<__nv_bfloat16> {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-  }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
-    uint4 v; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = v;
-  }
-};
 
 __device__ __forceinline__ bool is_halo(long long m, const Geom& g, int& n, int& y, int& x) {
   const int plane = g.plane();

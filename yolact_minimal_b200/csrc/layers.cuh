@@ -44,6 +44,7 @@ struct ConvArgs {
   int out_mode;          // 0: haloed NHWC act_dt, halo zeroed;  1: dense fp32 [B*H*W][Cout] (halo rows skipped)
   long long in_rows;     // total rows addressable in `in` (for bounds checks)
   int in_row_stride;     // tensor-core path: elements between consecutive rows of `in` (0 = Cin; < Cin = overlapping rows, stem)
+  long long w_ld;        // tensor-core path: elements between consecutive rows of `weight` (0 = ntaps*Cin_pad; larger = a tap subset of a wider matrix)
 };
 
 // run `expr` with type alias T bound to the C++ type of DType dt

@@ -32,6 +32,7 @@ struct ActBuf {
   int first = 0, last = 0;     // op indices (liveness)
   int slot = -1;
   bool dense_f32 = false;      // dense [B*H*W][C] fp32 scratch (head outputs)
+  int pad_rows = 0;            // extra pixel rows allocated behind the last image (stem space-to-depth image, see OP_STEM)
 };
 
 enum OpKind { OP_STEM, OP_POOL, OP_SPLIT, OP_CONV, OP_UPADD, OP_UP2X, OP_HEADFIN, OP_PATCH_EMBED, OP_LN, OP_ATTN, OP_MERGE_LN };
@@ -222,6 +223,11 @@ void build_program(yb_net* net) {
   // 64-channel materialised form that is otherwise only the fallback when the overlapping tensor map is refused.
   net->stem_wide = (getenv("YOLACT_B200_STEM_WIDE") || !tc_overlapping_rows_ok()) ? 1 : 0;
   const int stem_cols = new_act(net, net->stem_wide ? 64 : 16, net->H1);
+  // The 4-tap stem reads TWO pixel rows below an output row (dy = 3) and, through the overlapping tensor map, up to 3 pixels past
+  // a row: for the last image of a batch that is one pixel row (+4 pixels) BEHIND the image, which must read as zero.  The buffer
+  // carries that many spare rows and yb_net_forward zeroes them behind the batch's last image on every call (with fewer images
+  // than max_batch the region belongs to the next image slot and holds stale data; the arena slot is shared with other tensors).
+  net->acts[stem_cols].pad_rows = net->H1 + 2 + 4;
   { Op o; o.kind = OP_STEM; o.out = stem; o.aux = stem_cols; net->ops.push_back(o); }
   int x = new_act(net, 64, net->H2);
   { Op o; o.kind = OP_POOL; o.in = stem; o.out = x; net->ops.push_back(o); }
@@ -352,7 +358,7 @@ void plan_memory(yb_net* net) {
   for (auto& a : acts) {
     a.dt = a.dense_f32 ? DT_F32 : net->act_dt;
     const size_t rows = a.dense_f32 ? (size_t)net->max_batch * a.H * a.H : (size_t)net->max_batch * (a.H + 2) * (a.H + 2) * a.planes;
-    a.bytes = align_up(rows * a.C * (a.dense_f32 ? 4 : esz), 1024);
+    a.bytes = align_up((rows + a.pad_rows) * a.C * (a.dense_f32 ? 4 : esz), 1024);
   }
   std::vector<int> slot_free_at;                                   // op index after which the slot is free
   net->slot_bytes.clear();
@@ -610,7 +616,7 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
       a.ntaps = 4; a.relu = 1; a.out_mode = 0;
       for (int dy = 0; dy < 4; ++dy) a.tap_shift[dy] = (dy - 1) * (net->H1 + 2) - 1;
       a.in_rows = (long long)max_batch * (net->H1 + 2) * (net->H1 + 2);
-      if (!net->stem_wide) { a.in_row_stride = 16; a.in_rows -= 3; }   // rows overlap: row p = pixels p .. p+3
+      if (!net->stem_wide) a.in_row_stride = 16;                      // rows overlap: row p = pixels p .. p+3 (3 spare pixels exist: pad_rows)
       YB_PROPAGATE(tc_plan_create(a, max_batch, &so.tc));
     }
     for (auto& o : net->ops) {
@@ -664,6 +670,10 @@ extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* c
       case OP_STEM:
         if (o.tc) {
           YB_PROPAGATE(launch_stem_s2d(img, act_ptr(net, o.aux), net->act_dt, net->stem_wide, batch, cfg.img_size, net->H1, s));
+          {  // zero the pixel row (+4 pixels) behind the batch's last image: the dy = 3 taps of its bottom row land there
+            const size_t px = (size_t)(net->stem_wide ? 64 : 16) * dtype_size(net->act_dt), Wp1 = (size_t)net->H1 + 2;
+            YB_CHECK_CUDA(cudaMemsetAsync((char*)act_ptr(net, o.aux) + (size_t)batch * Wp1 * Wp1 * px, 0, (Wp1 + 4) * px, s));
+          }
           ConvArgs a = net->stem_args;
           a.B = batch;
           YB_PROPAGATE(launch_conv_tc(o.tc, a, s));

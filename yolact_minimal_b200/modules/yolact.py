@@ -6,8 +6,8 @@ proto_out [B,P,P,32])`.  The submodules are parameter containers; the forward pa
 CUDA layer program in libyolact_b200.so, driven through yolact_minimal_b200.engine.Engine.
 
 Backbones: ResNet-50/101 and Swin-T (`swin_tiny_*` configs).  In training mode forward returns the
-reference's four losses (modules/yolact.py:159-161,:166-313) through train_torch.py -- a first cut on
-torch autograd (not the native path), ResNet backbones only.
+reference's four losses (modules/yolact.py:159-161,:166-313) computed -- with their backward pass -- by the
+native training engine (train_native.py -> csrc/train.cu), ResNet backbones.
 """
 import math
 import os
@@ -120,9 +120,9 @@ class Yolact(nn.Module):
 
     def forward(self, img, box_classes=None, masks_gt=None):
         if self.training:
-            # first cut of the training branch: ATen/cuDNN forward + autograd + the four losses (train_torch.py)
-            from ..train_torch import training_step_forward
-            return training_step_forward(self, img, box_classes, masks_gt)
+            # native training engine (csrc/train.cu): forward, targets, losses and backward in libyolact_b200.so
+            from ..train_native import training_step
+            return training_step(self, img, box_classes, masks_gt)
         if not img.is_cuda:
             raise RuntimeError('yolact_minimal_b200.Yolact runs on CUDA only (no CPU fallback): move the model and input to the GPU')
         return self.engine(img.shape[0]).forward(img)
