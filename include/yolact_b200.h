@@ -67,6 +67,7 @@ typedef struct {
   int coef_dim;       /* 32 */
   int traditional;    /* cfg.traditional_nms: 0 = Fast-NMS, 1 = per-class greedy NMS in pixel coords */
   float img_size;     /* cfg.img_size, only used when traditional != 0 */
+  int no_clip;        /* 0: clip decoded boxes to [0,1] (nms(), output_utils.py:153); 1: no clip -- the ONNX/TRT callers' nms_numpy (:186-190) */
 } yb_detect_params;
 
 YB_API size_t yb_detect_workspace_bytes(int batch, int num_anchors, const yb_detect_params* p);
@@ -101,8 +102,8 @@ YB_API int yb_hard_nms_host(const float* dets, int n, float thresh, uint8_t* out
  * Mask assembly -- replaces utils/output_utils.py:217-231 (after_nms) + box_utils.py:147-168.
  *   masks = sigmoid(proto[P,P,K] @ coef[d,K]^T); crop to box (+1 px pad); bilinear resize to
  *   max(h,w)^2 (align_corners=False); > 0.5; slice to h x w; boxes*max(h,w) -> int32 (trunc).
- * proto [P,P,K], coef [d,K], box [d,4]; out_mask [d,img_h,img_w] (uint8 0/1 when
- * mask_f32 == 0, float32 0/1 otherwise -- the reference's dtype); out_box_px [d,4] int32.
+ * proto [P,P,K], coef [d,K], box [d,4]; out_mask [d,img_h,img_w] (mask_f32 = 0: uint8 0/1; 1: float32 0/1 -- the reference's
+ * dtype; 2: BIT-PACKED uint32 words [d,img_h,ceil(img_w/32)], pixel x = bit x & 31 of word x >> 5); out_box_px [d,4] int32.
  * workspace: d*P*P floats.
  * ---------------------------------------------------------------------------------------- */
 YB_API size_t yb_mask_workspace_bytes(int num_det, int proto_size);
@@ -110,6 +111,20 @@ YB_API int yb_mask_assemble(const float* proto, const float* coef, const float* 
                      int proto_size, int coef_dim, int img_h, int img_w, int crop, int mask_f32,
                      void* workspace, size_t workspace_bytes,
                      void* out_mask, int32_t* out_box_px, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mask output stage -- what the reference's evaluation loop does with the masks after after_nms:
+ *   yb_pack_mask_bits   {0,1} masks [n,h,w] (uint8, or float32 when is_f32) -> packed words [n,h,ceil(w/32)]
+ *   yb_mask_iou_bits    utils/box_utils.py:189-200 mask_iou on packed masks: out [n,m] = |a&b| / (|a| + |b| - |a&b|); `words` = words per mask
+ *   yb_box_iou          utils/box_utils.py:8-37 box_iou for [n,4] x [m,4] corner boxes -> [n,m]
+ *   yb_mask_rle         the run lengths of pycocotools.mask.encode(np.asfortranarray(mask)) (utils/common_utils.py:88-96): column-major
+ *                       scan, first count = leading zeros (possibly 0).  counts [n,max_runs] uint32, nruns [n] (negative = -needed
+ *                       when max_runs is too small).  The ASCII compression of the counts is host work (utils/mask_utils.py).
+ * ---------------------------------------------------------------------------------------- */
+YB_API int yb_pack_mask_bits(const void* masks, int is_f32, int n, int h, int w, uint32_t* out, void* stream);
+YB_API int yb_mask_iou_bits(const uint32_t* a, int n, const uint32_t* b, int m, int64_t words, float* out, void* stream);
+YB_API int yb_box_iou(const float* a, int n, const float* b, int m, float* out, void* stream);
+YB_API int yb_mask_rle(const uint32_t* bits, int n, int h, int w, uint32_t* counts, int max_runs, int32_t* nruns, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-process -- replaces utils/augmentations.py:219-227 val_aug(img, val_size):

@@ -316,3 +316,43 @@ def val_aug(img_bgr_u8, val_size):
     out = (rows0 * ay0[:, None, None] + rows1 * ay1[:, None, None]).astype(F32)
     out = (out - NORM_MEAN) / NORM_STD
     return np.ascontiguousarray(out[:, :, ::-1].transpose(2, 0, 1)).astype(F32)
+
+
+# ----------------------------------------------------------------------------- numpy twins / mask output stage
+def nms_numpy(class_pred, box_pred, anchors, score_thre=0.05, iou_thre=0.5, top_k=200, max_det=100):
+    """utils/output_utils.py:166-197 for ONE image: nms() WITHOUT the clip of the decoded boxes to [0,1] (compare :186-190 with
+    :153).  fp32 restatement (the reference's twin decodes in float64 because its anchors are a float64 array: agreement ~1e-7)."""
+    class_p = np.ascontiguousarray(class_pred.astype(F32, copy=False).T)[1:, :]
+    keep = class_p.max(axis=0) > F32(score_thre)
+    if not keep.any():
+        return None
+    cand_anchor = np.nonzero(keep)[0]
+    b, a = box_pred[keep].astype(F32), anchors[keep].astype(F32)
+    xy = a[:, :2] + b[:, :2] * F32(0.1) * a[:, 2:]
+    wh = a[:, 2:] * exp_f32(b[:, 2:] * F32(0.2))
+    out = np.concatenate((xy, wh), axis=1).astype(F32)
+    out[:, :2] -= out[:, 2:] / F32(2)
+    out[:, 2:] += out[:, :2]
+    return fast_nms(out, class_p[:, keep], cand_anchor, top_k, iou_thre, max_det)
+
+
+def rle_counts(mask):
+    """Run lengths of pycocotools.mask.encode(np.asfortranarray(mask)) for ONE {0,1} mask [h,w]: column-major scan, alternating
+    runs starting with a (possibly empty) run of zeros (pycocotools/common/maskApi.c rleEncode)."""
+    v = np.asarray(mask).astype(np.uint8).reshape(-1, order='F')
+    counts, prev, run = [], 0, 0
+    for x in v:
+        if x != prev:
+            counts.append(run); run = 0; prev = x
+        run += 1
+    counts.append(run)
+    return np.asarray(counts, dtype=np.uint32)
+
+
+def rle_decode(counts, h, w):
+    v = np.zeros(h * w, np.uint8)
+    p, val = 0, 0
+    for c in counts:
+        v[p:p + int(c)] = val
+        p += int(c); val ^= 1
+    return v.reshape(h, w, order='F')

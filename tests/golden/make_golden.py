@@ -177,6 +177,33 @@ def gen_after_nms(rcfg, rout):
     np.savez_compressed(os.path.join(HERE, 'after_nms.npz'), **out)
 
 
+def gen_numpy_twins(rcfg, rout):
+    """The ONNX / TRT callers' numpy post-process (utils/output_utils.py:46-81,:166-197,:236-273), run by the reference itself:
+    nms_numpy (no clip of the decoded boxes) and after_nms_numpy (cv2 resize, boolean masks)."""
+    out = {}
+    cfg = ref_cfg(rcfg, 'res101_coco', 544)
+    cfg.traditional_nms = False
+    for name, S, regime, seed, h, w in (('stress_S128', 128, 'stress', 1, 80, 120), ('realistic_S256', 256, 'realistic', 2, 97, 64),
+                                        ('wild_S128', 128, 'stress', 4, 60, 60)):
+        anchors = pp.make_anchors(S)
+        cls, box, coef = synth.head_outputs(seed, anchors.shape[0], 81, regime)
+        if name.startswith('wild'):
+            box = (box * 3).astype(np.float32)                   # boxes far outside [0,1]: the missing clip matters
+        proto = synth.proto(seed, S // 4)
+        r = rout.nms_numpy(cls[None], box[None], coef[None], proto[None], anchors.reshape(-1).tolist(), cfg)
+        ids, scores, boxes, coefs, _ = r
+        out[name + '/class'] = np.asarray(ids, np.int64); out[name + '/score'] = np.asarray(scores, np.float32)
+        out[name + '/box'] = np.asarray(boxes, np.float64); out[name + '/coef'] = np.asarray(coefs, np.float32)
+        o = pp.nms_numpy(cls, box, anchors)
+        assert np.array_equal(o[0], out[name + '/class']) and np.array_equal(o[1], out[name + '/score']), name
+        assert np.allclose(o[2], out[name + '/box'], rtol=0, atol=1e-5), name
+        rid, rsc, rbx, rmask = rout.after_nms_numpy(ids, scores, np.asarray(boxes, np.float32).copy(), coefs, proto, h, w, cfg)
+        out[name + '/boxes_px'] = rbx.astype(np.int32)
+        out[name + '/mask_bits'] = np.packbits(rmask.astype(np.uint8)); out[name + '/mask_shape'] = np.asarray(rmask.shape, np.int64)
+        print(f'  numpy twins {name}: {len(ids)} dets, box range [{float(np.min(boxes)):.2f}, {float(np.max(boxes)):.2f}], masks {rmask.shape}, oracle == reference')
+    np.savez_compressed(os.path.join(HERE, 'numpy_twins.npz'), **out)
+
+
 def gen_anchors(rcfg, ryolact):
     out = {}
     for S in (128, 384, 400, 544, 550, 576):
@@ -378,7 +405,7 @@ if __name__ == '__main__':
     torch.set_num_threads(os.cpu_count())
     build_cython_nms()
     rcfg, ryolact, rout, rbox = import_reference()
-    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug', 'train', 'surface', 'stages']
+    which = sys.argv[1:] or ['anchors', 'hard', 'post', 'after', 'forward', 'valaug', 'train', 'surface', 'stages', 'twins']
     if 'anchors' in which: gen_anchors(rcfg, ryolact)
     if 'hard' in which: gen_hard_nms()
     if 'post' in which: gen_postprocess(rcfg, rout)
@@ -388,4 +415,5 @@ if __name__ == '__main__':
     if 'train' in which: gen_train(rcfg, ryolact)
     if 'surface' in which: gen_surface(rcfg, ryolact)
     if 'stages' in which: gen_train_stages(rcfg, ryolact, rbox)
+    if 'twins' in which: gen_numpy_twins(rcfg, rout)
     print('done')

@@ -52,7 +52,7 @@ def test_header_is_plain_c_and_links_without_torch(tmp_path):
     src = tmp_path / 'demo.c'
     src.write_text('#include <stdio.h>\n#include "yolact_b200.h"\n'
                    'int main(void) {\n'
-                   '  yb_detect_params p = {0.05f, 0.5f, 200, 100, 81, 32, 0, 550.0f};\n'
+                   '  yb_detect_params p = {0.05f, 0.5f, 200, 100, 81, 32, 0, 550.0f, 0};\n'
                    '  printf("%d %zu\\n", yb_version(), yb_detect_workspace_bytes(1, 19248, &p));\n'
                    '  return yb_detect(0, 0, 0, 0, 1, 19248, &p, 0, 0, 0, 0, 0, 0, 0, 0, 0) == YB_OK;   /* NULL pointers must be refused */\n'
                    '}\n')

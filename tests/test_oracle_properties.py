@@ -112,3 +112,20 @@ def test_shards_tile_the_batch(B, W):
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     sizes = [e - s for s, e in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_rle_oracle_round_trip_and_string_compression():
+    """The RLE checker (oracle/postprocess_np.rle_counts, a restatement of pycocotools' rleEncode on Fortran-ordered masks) and the
+    product's host-side ASCII compression (utils/mask_utils.py, pycocotools' rleToString / rleFrString) round-trip."""
+    from yolact_minimal_b200.utils import mask_utils as mu
+    from oracle import synth, postprocess_np as pp
+    import numpy as np
+    for seed, (h, w) in enumerate(((5, 7), (33, 20), (1, 64), (64, 1))):
+        m = (synth.uniform(40 + seed, 1, (h, w)) > 0.6).astype(np.uint8)
+        c = pp.rle_counts(m)
+        assert int(c.sum()) == h * w and np.array_equal(pp.rle_decode(c, h, w), m)
+        assert mu.rle_string_to_counts(mu.rle_counts_to_string(c)) == [int(x) for x in c]
+    assert list(pp.rle_counts(np.zeros((3, 4), np.uint8))) == [12] and list(pp.rle_counts(np.ones((3, 4), np.uint8))) == [0, 12]
+    # known value: counts with a long run and a decreasing tail exercise the sign-extended difference coding
+    c = [0, 5, 3, 70000, 2, 1, 9]
+    assert mu.rle_string_to_counts(mu.rle_counts_to_string(c)) == c

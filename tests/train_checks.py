@@ -58,15 +58,15 @@ def run_native_losses(dev, cfg, anchors, tg, mk, class_p, box_p, coef_p, proto_p
 
 
 def torch_losses_and_grads(cfg, anchors, tg, mk, class_p, box_p, coef_p, proto_p, seg_p, grad_scale=(1, 1, 1, 1)):
-    """The checker: oracle/train_torch.py's four losses and torch-autograd gradients w.r.t. the five network outputs (fp64 on CPU)."""
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).double().requires_grad_(True)
+    """The checker: oracle/train_torch.py's four losses and torch-autograd gradients w.r.t. the five network outputs (fp32 on CPU)."""
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().requires_grad_(True)
     cls, box, coef, proto, seg = t(class_p), t(box_p), t(coef_p), t(proto_p), t(seg_p)
-    anc = torch.from_numpy(anchors).double()
+    anc = torch.from_numpy(anchors).float()
     B = class_p.shape[0]
-    out = [tt.assign_targets(cfg, torch.from_numpy(tg[i][:, :4]).double(), anc, torch.from_numpy(tg[i][:, 4]).long()) for i in range(B)]
+    out = [tt.assign_targets(cfg, torch.from_numpy(tg[i][:, :4]).float(), anc, torch.from_numpy(tg[i][:, 4]).long()) for i in range(B)]
     offsets, labels, matched, idx = (torch.stack(x) for x in zip(*out))
     pos = labels > 0
-    masks = [torch.from_numpy(m).double() for m in mk]
+    masks = [torch.from_numpy(m).float() for m in mk]
     losses = (tt.category_loss(cfg, cls, labels, pos), tt.box_loss(cfg, box, offsets, pos), tt.mask_loss(cfg, pos, idx, coef, proto, masks, matched),
               tt.semantic_loss(cfg, seg, masks, [torch.from_numpy(x[:, 4]).long() for x in tg]))
     sum(w * l for w, l in zip(grad_scale, losses)).backward()

@@ -17,7 +17,7 @@ vp = C.c_void_p
 
 class DetectParams(C.Structure):
     _fields_ = [('score_thr', C.c_float), ('iou_thr', C.c_float), ('top_k', C.c_int), ('max_det', C.c_int),
-                ('num_classes', C.c_int), ('coef_dim', C.c_int), ('traditional', C.c_int), ('img_size', C.c_float)]
+                ('num_classes', C.c_int), ('coef_dim', C.c_int), ('traditional', C.c_int), ('img_size', C.c_float), ('no_clip', C.c_int)]
 
 
 class ProfEntry(C.Structure):
@@ -60,6 +60,10 @@ PROTOTYPES = {
     'yb_mask_assemble': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    vp, C.c_size_t, vp, vp, vp]),
     'yb_val_aug': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    'yb_pack_mask_bits': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    'yb_mask_iou_bits': (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int64, vp, vp]),
+    'yb_box_iou': (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp]),
+    'yb_mask_rle': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
     'yb_net_create': (C.c_int, [C.POINTER(NetConfig), C.POINTER(vp)]),
     'yb_net_destroy': (None, [vp]),
     'yb_net_num_params': (C.c_int, [vp]),

@@ -183,6 +183,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
 }
+// MN-major, 128B-swizzled operand tile (the weight-gradient GEMM's B operand, read straight from the [pixels][channels] activations):
+// the tile is BN/64 TMA boxes of [64 k-rows][64 channels] (8 KiB each); a row of 128 bytes holds 64 consecutive MN elements of one k,
+// 8 k-rows form a 1 KiB swizzle atom (stride byte offset 1024), the next 64-element MN chunk is the next box (leading byte offset 8192).
+// Canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address
+  d |= (uint64_t)(8192 >> 4) << 16;                   // leading byte offset: between 64-element MN chunks
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: between groups of 8 k-rows
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
 // The MMA warp runs its loops with all 32 lanes (warp-uniform control flow and operands, so descriptors and addresses stay
 // in uniform registers); only the tcgen05 instructions themselves are predicated on the one elected lane (`issue`).  Issued from
 // inside an `if (lane == 0)` region instead, every MMA costs an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence of ~15 dependent
@@ -488,7 +501,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else {
               mbar_expect_tx(&full[stage], tx);
               tma_load_2d(sA + (size_t)stage * TC_A_STAGE, &tmA, kb * TC_BK, row, &full[stage]);
-              if (!p.b_resident) tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK + bcol0, n0, &full[stage]);
+              if (p.gemm) {                                          // MN-major B: BN/64 boxes [64 k-rows][64 channels] at k-row kb*64 + tap shift
+                for (int j = 0; j < p.BN / 64; ++j)
+                  tma_load_2d(sB + (size_t)stage * b_stage + (size_t)j * 8192, &tmB, n0 + j * 64, kb * TC_BK + bcol0, &full[stage]);
+              } else if (!p.b_resident) tma_load_2d(sB + (size_t)stage * b_stage, &tmB, (t * p.kb_per_tap + kb) * TC_BK, n0, &full[stage]);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -553,12 +569,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
-          const uint64_t db = umma_desc(smem_u32(sB + (size_t)(p.b_resident ? kb : stage) * b_stage));
+          const uint32_t b_addr = smem_u32(sB + (size_t)(p.b_resident ? kb : stage) * b_stage);
+          const uint64_t db = p.gemm ? umma_desc_mn(b_addr) : umma_desc(b_addr);
+          const uint32_t idesc_k = p.gemm ? (idesc | (1u << 16)) : idesc;            // gemm: B is MN-major
+          const uint64_t bstep = p.gemm ? 128u : 2u;                                 // 16 k-rows = 2 KiB (MN-major) / 32 bytes (K-major), >> 4
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u, issue);
-            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u, issue);
+            if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)k * bstep, idesc_k, (kb | k) != 0 ? 1u : 0u, issue);
+            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)k * bstep, idesc_k, (kb | k) != 0 ? 1u : 0u, issue);
           }
           if (PAIR) umma_commit_pair(&empty[stage], issue); else umma_commit(&empty[stage], issue);   // smem stage free (in both CTAs) once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -915,14 +934,13 @@ static int tc_device_setup(int* sms) {
 // ---- plain GEMM over long K on the same kernel (weight gradients; see TcParams::gemm) ---------------------------
 int tc_plan_create_gemm(const GemmArgs& g, TcPlan** out) {
   YB_REQUIRE(g.act_dt == DT_BF16 || g.act_dt == DT_F16, YB_ERR_UNSUPPORTED, "tc_plan_create_gemm: 16-bit operands only");
-  YB_REQUIRE(g.M >= 1 && g.K >= 1 && g.lda % 8 == 0 && g.ldb % 8 == 0 && g.ntaps >= 1 && g.ntaps <= 16, YB_ERR_INVALID,
+  YB_REQUIRE(g.M >= 1 && g.K >= 1 && g.lda % 8 == 0 && g.ldb % 8 == 0 && g.ldb >= g.Nper && g.ntaps >= 1 && g.ntaps <= 16, YB_ERR_INVALID,
              "tc_plan_create_gemm: M=%d K=%d lda=%d ldb=%d ntaps=%d", g.M, g.K, g.lda, g.ldb, g.ntaps);
   int bn = 0;
   if (g.Nper % 256 == 0) bn = 256;
-  else if (g.Nper <= 256 && g.Nper % 16 == 0) bn = g.Nper;
   else if (g.Nper % 128 == 0) bn = 128;
   else if (g.Nper % 64 == 0) bn = 64;
-  YB_REQUIRE(bn != 0, YB_ERR_UNSUPPORTED, "tc_plan_create_gemm: N per tap = %d has no tile", g.Nper);
+  YB_REQUIRE(bn != 0, YB_ERR_UNSUPPORTED, "tc_plan_create_gemm: N per tap = %d is not a multiple of 64", g.Nper);
   TcPlan* pl = new TcPlan();
   pl->gemm = 1; pl->BN = bn;
   int cols = 32;
@@ -937,7 +955,8 @@ int tc_plan_create_gemm(const GemmArgs& g, TcPlan** out) {
   pl->smem_bytes = (size_t)pl->stages * per_stage + 2048;
   const bool f16 = g.act_dt == DT_F16;
   int s = make_map(&pl->tmA, g.a, (uint64_t)g.K, (uint64_t)g.M, TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)g.lda);
-  if (s == YB_OK) s = make_map(&pl->tmB, g.b, (uint64_t)g.Kb, (uint64_t)g.Nper, (uint32_t)bn, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)g.ldb);
+  // B is read MN-major straight from the [Kb pixels][ldb channels] activations: boxes of [64 k-rows][64 channels]
+  if (s == YB_OK) s = make_map(&pl->tmB, g.b, (uint64_t)g.Nper, (uint64_t)g.Kb, 64, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)g.ldb);
   pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;
   if (s == YB_OK) s = tc_device_setup(&pl->sms);
   if (s != YB_OK) { delete pl; return s; }

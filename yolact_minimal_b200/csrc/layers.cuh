@@ -65,8 +65,9 @@ void tc_plan_destroy(TcPlan* p);
 int launch_conv_tc(const TcPlan* p, const ConvArgs& a, cudaStream_t s);
 bool tc_supported(const ConvArgs& a);
 
-// plain GEMM over a long K on the tcgen05 kernel (weight gradients):  out[M][ntaps*Nper] (+)= A[M][K] x B_tap[Nper][K]^T, fp32 out,
-// both operands 16-bit and K-major (row = output index, columns = K); tap t reads B at columns k + shift[t] (zero outside [0, Kb)).
+// plain GEMM over a long K on the tcgen05 kernel (weight gradients):  out[M][ntaps*Nper] (+)= sum_k A[M][k] * B[k + shift_tap][Nper], fp32 out.
+// A (the TRANSPOSED output gradient) is K-major [M][lda]; B (the activations as they are: [Kb pixel rows][ldb channels]) is read MN-major,
+// tap t at pixel row k + shift[t] (rows outside [0, Kb) read as zero) -- a row shift, because TMA wants 16-byte aligned inner coordinates.
 struct GemmArgs {
   const void* a; const void* b; float* out;
   int act_dt, M, Nper, K, lda, ldb, ntaps, accumulate;

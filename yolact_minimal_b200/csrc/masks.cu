@@ -98,6 +98,28 @@ k_mask_resize(const float* __restrict__ low, int d, int P, int ori, int img_h, i
   out[((size_t)det * img_h + oy) * img_w + ox] = (OutT)(v > 0.5f ? 1 : 0);
 }
 
+// bit-packed output: one thread = one 32-pixel word of an output row (1 bit / pixel: 32x less HBM write traffic than float32 masks)
+__global__ void __launch_bounds__(kMaskThreads)
+k_mask_resize_bits(const float* __restrict__ low, int P, int ori, int img_h, int img_w, int words, uint32_t* __restrict__ out) {
+  const int det = blockIdx.z, oy = blockIdx.y, wi = blockIdx.x * kMaskThreads + threadIdx.x;
+  if (wi >= words) return;
+  const float scale = __fdiv_rn((float)P, (float)ori);
+  int y0, y1; float ly0, ly1;
+  bilinear_src(oy, scale, P, y0, y1, ly0, ly1);
+  const float* r0 = low + ((size_t)det * P + y0) * P;
+  const float* r1 = low + ((size_t)det * P + y1) * P;
+  uint32_t v = 0;
+  const int cnt = min(32, img_w - wi * 32);
+  for (int b = 0; b < cnt; ++b) {
+    int x0, x1; float lx0, lx1;
+    bilinear_src(wi * 32 + b, scale, P, x0, x1, lx0, lx1);
+    const float top = __fadd_rn(__fmul_rn(lx0, r0[x0]), __fmul_rn(lx1, r0[x1]));
+    const float bot = __fadd_rn(__fmul_rn(lx0, r1[x0]), __fmul_rn(lx1, r1[x1]));
+    v |= (__fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot)) > 0.5f ? 1u : 0u) << b;
+  }
+  out[((size_t)det * img_h + oy) * words + wi] = v;
+}
+
 __global__ void k_boxes_px(const float* __restrict__ box, int n4, float ori, int32_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) out[i] = (int32_t)__fmul_rn(box[i], ori);      // .int() truncates toward zero
@@ -130,7 +152,10 @@ extern "C" int yb_mask_assemble(const float* proto, const float* coef, const flo
       proto, coef, box, num_det, P, coef_dim, crop, low);
   YB_CHECK_LAUNCH();
   dim3 grid(ceil_div(img_w, kMaskThreads), img_h, num_det);
-  if (mask_f32) k_mask_resize<float><<<grid, kMaskThreads, 0, stream>>>(low, num_det, P, ori, img_h, img_w, (float*)out_mask);
+  if (mask_f32 == 2) {
+    const int words = (img_w + 31) / 32;
+    k_mask_resize_bits<<<dim3(ceil_div(words, kMaskThreads), img_h, num_det), kMaskThreads, 0, stream>>>(low, P, ori, img_h, img_w, words, (uint32_t*)out_mask);
+  } else if (mask_f32 == 1) k_mask_resize<float><<<grid, kMaskThreads, 0, stream>>>(low, num_det, P, ori, img_h, img_w, (float*)out_mask);
   else k_mask_resize<uint8_t><<<grid, kMaskThreads, 0, stream>>>(low, num_det, P, ori, img_h, img_w, (uint8_t*)out_mask);
   YB_CHECK_LAUNCH();
   k_boxes_px<<<ceil_div(num_det * 4, 128), 128, 0, stream>>>(box, num_det * 4, (float)ori, out_box_px);

@@ -57,7 +57,7 @@ static size_t carve(DetectWs* w, char* base, int B, int A, int C1, int KC) {
 __device__ __forceinline__ float clip01(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }  // NaN stays NaN
 
 // utils/output_utils.py:148-153
-__device__ __forceinline__ float4 decode_box(float4 b, float4 a) {
+__device__ __forceinline__ float4 decode_box(float4 b, float4 a, int no_clip) {
   float cx = __fadd_rn(a.x, __fmul_rn(__fmul_rn(b.x, 0.1f), a.z));
   float cy = __fadd_rn(a.y, __fmul_rn(__fmul_rn(b.y, 0.1f), a.w));
   // correctly-rounded fp32 exp (fp64 exp rounded once) -- matches oracle/postprocess_np.exp_f32
@@ -69,6 +69,7 @@ __device__ __forceinline__ float4 decode_box(float4 b, float4 a) {
   float y1 = __fsub_rn(cy, __fmul_rn(h, 0.5f));
   float x2 = __fadd_rn(w, x1);
   float y2 = __fadd_rn(h, y1);
+  if (no_clip) return make_float4(x1, y1, x2, y2);                 // the numpy twin nms_numpy has no clip (output_utils.py:186-190)
   return make_float4(clip01(x1), clip01(y1), clip01(x2), clip01(y2));
 }
 
@@ -103,7 +104,7 @@ __device__ __forceinline__ float ovr_plus1(float4 a, float area_a, float4 b, flo
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, const float* __restrict__ anchors,
-                int A, int C, float score_thr, DetectWs ws) {
+                int A, int C, float score_thr, int no_clip, DetectWs ws) {
   extern __shared__ float tile[];                 // [kP1Anchors * C]
   __shared__ int s_kept[kP1Anchors];
   __shared__ int s_warp_cnt[kThreads / 32];
@@ -159,7 +160,7 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
     ws.cand_anchor[slot] = a;
     const float4 bb = __ldg(reinterpret_cast<const float4*>(box) + (size_t)b * A + a);
     const float4 an = __ldg(reinterpret_cast<const float4*>(anchors) + a);
-    ws.cand_box[slot] = decode_box(bb, an);
+    ws.cand_box[slot] = decode_box(bb, an, no_clip);
   }
   __syncthreads();
   // class-major write: warp w takes classes w, w+8, ...; lanes run over the kept anchors
@@ -698,7 +699,7 @@ extern "C" int yb_detect(const float* cls, const float* box, const float* coef, 
     const size_t smem = (size_t)kP1Anchors * C * sizeof(float);
     YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(A, kP1Anchors), B);
-    k_filter_decode<<<grid, kThreads, smem, stream>>>(cls, box, anchors, A, C, p->score_thr, ws);
+    k_filter_decode<<<grid, kThreads, smem, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
     YB_CHECK_LAUNCH();
   }
   if (!p->traditional) {

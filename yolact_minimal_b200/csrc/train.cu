@@ -79,6 +79,8 @@ struct yb_train {
   std::vector<void*> allocs;
   std::vector<TcPlan*> plans;
   std::vector<Launch> fwd, bwd, bwd_tail;
+  std::vector<std::string> fwd_what, bwd_what;     // debug labels (YOLACT_B200_TRAIN_DEBUG=1 synchronises after every launch)
+  std::string cur_label;
   std::vector<std::function<int()>> bwd_builders;     // run in reverse op order when the program is finalised
   std::vector<PackDesc> pack_descs;
   std::vector<UnpackDesc> unpack_descs;
@@ -111,6 +113,9 @@ struct yb_train {
 };
 
 namespace {
+
+#define FWD_PUSH(...) do { t->fwd_what.push_back(t->cur_label + " @" + std::to_string(__LINE__)); t->fwd.push_back(__VA_ARGS__); } while (0)
+#define BWD_PUSH(...) do { t->bwd_what.push_back(t->cur_label + " @" + std::to_string(__LINE__)); t->bwd.push_back(__VA_ARGS__); } while (0)
 
 int dev_alloc(yb_train* t, void** p, size_t bytes) {
   YB_CHECK_CUDA(cudaMalloc(p, bytes ? bytes : 16));
@@ -241,6 +246,7 @@ void fill_taps_fwd(const ConvRec* c, int Wp, long long plane_rows, int* ntaps, i
 // x: input (haloed, planes == 1); returns y (raw conv output + bias, optional fused ReLU; haloed 16-bit, or dense fp32 [B*Ho*Ho][Cout_pad])
 int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std::string& yname, TT** out, TT* y_given = nullptr) {
   const int B = t->B, Hin = x->H, Hout = c->stride == 2 ? (Hin - 1) / 2 + 1 : Hin, Wp = Hout + 2;
+  t->cur_label = "conv " + yname;
   const long long plane_rows = (long long)B * Wp * Wp;
   TT* src = x;
   if (c->stride == 2) {
@@ -249,7 +255,7 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
     YB_PROPAGATE(alloc_data(t, src));
     void* xin = x->data; void* pout = src->data;
     const int dt = t->dt, Cin = c->Cin;
-    t->fwd.push_back([=](cudaStream_t s) { return launch_phase_split(xin, pout, dt, B, Cin, Hin, Hout, planes, plane_rows, s); });
+    FWD_PUSH([=](cudaStream_t s) { return launch_phase_split(xin, pout, dt, B, Cin, Hin, Hout, planes, plane_rows, s); });
   }
   TT* y = y_given;
   if (!y) {
@@ -269,7 +275,7 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
   YB_PROPAGATE(tc_plan_create(a, B, &pl));
   t->plans.push_back(pl);
   const int bias_idx = c->bias_idx;
-  t->fwd.push_back([=](cudaStream_t s) {
+  FWD_PUSH([=](cudaStream_t s) {
     ConvArgs aa = a;
     if (bias_idx >= 0) aa.bias = t->bound[bias_idx].data;
     return launch_conv_tc(pl, aa, s);
@@ -278,6 +284,7 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
   // ---------------- backward (built later, in reverse op order) ----------------
   t->bwd_builders.push_back([=]() -> int {
     const int dt = t->dt;
+    t->cur_label = "conv-bwd " + y->name;
     YB_REQUIRE(y->grad != nullptr && y->grad_set, YB_ERR_STATE, "train: conv output %s has no gradient", y->name.c_str());
     const int Cg = y->Cg;                                            // channels of dY (== Cout_pad except padded small outputs)
     void* dy = y->grad;
@@ -285,12 +292,12 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
     if (relu == 1 && !out_dense) {                                   // z = relu(conv + b): dY = dz * [z > 0]   (dense outputs are masked by their producer)
       void* z = y->data;
       const long long n = rows_y * Cg;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_relu_bwd(dy, z, dt, n, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_relu_bwd(dy, z, dt, n, s); });
     }
     // bias gradient
     if (!c->bname.empty() || !c->cat.empty()) {
       float* bs = c->bsum;                                           // offset into the per-step zeroed statistics arena
-      t->bwd.push_back([=](cudaStream_t s) { return launch_colstats(dy, dt, rows_y, Cg, (float*)((char*)t->stats + (size_t)bs), s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_colstats(dy, dt, rows_y, Cg, (float*)((char*)t->stats + (size_t)bs), s); });
     }
     // weight gradient: dW[co][tap][ci] = sum_m dY[m][co] * X[m + shift_tap][ci]
     {
@@ -298,23 +305,16 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
       void* dyT = nullptr;
       YB_PROPAGATE(dev_alloc(t, &dyT, (size_t)c->Cout_pad * ldT * 2));
       const int Mrows = c->Cout_pad;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_transpose16(dy, Cg, dyT, dt, rows_y, Mrows, ldT, s); });
-      if (!src->tr_done) {
-        src->ldT = (src->rows + 7) / 8 * 8;
-        YB_PROPAGATE(dev_alloc(t, &src->tr, (size_t)src->C * src->ldT * 2));
-        void* xd = src->data; void* xt = src->tr; const long long xr = src->rows, xl = src->ldT; const int xc = src->C;
-        t->bwd.push_back([=](cudaStream_t s) { return launch_transpose16(xd, xc, xt, dt, xr, xc, xl, s); });
-        src->tr_done = true;
-      }
+      BWD_PUSH([=](cudaStream_t s) { return launch_transpose16(dy, Cg, dyT, dt, rows_y, Mrows, ldT, s); });
       GemmArgs g; memset(&g, 0, sizeof(g));
-      g.a = dyT; g.b = src->tr; g.out = c->dWp; g.act_dt = dt; g.M = c->Cout_pad; g.Nper = c->Cin_pad; g.K = (int)rows_y; g.lda = (int)ldT; g.ldb = (int)src->ldT;
+      g.a = dyT; g.b = src->data; g.out = c->dWp; g.act_dt = dt; g.M = c->Cout_pad; g.Nper = c->Cin_pad; g.K = (int)rows_y; g.lda = (int)ldT; g.ldb = src->C;
       g.Kb = src->rows; g.accumulate = c->wgrad_set ? 1 : 0;
       fill_taps_fwd(c, Wp, plane_rows, &g.ntaps, g.shift);
       YB_REQUIRE(c->Cin == c->Cin_pad, YB_ERR_UNSUPPORTED, "train: conv %s Cin=%d is not a multiple of 64", c->wname.c_str(), c->Cin);
       TcPlan* gp = nullptr;
       YB_PROPAGATE(tc_plan_create_gemm(g, &gp));
       t->plans.push_back(gp);
-      t->bwd.push_back([=](cudaStream_t s) { return launch_gemm_tc(gp, g, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_gemm_tc(gp, g, s); });
       c->wgrad_set = true;
     }
     // input gradient
@@ -331,7 +331,7 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
         TcPlan* dp = nullptr;
         YB_PROPAGATE(tc_plan_create(d, B, &dp));
         t->plans.push_back(dp);
-        t->bwd.push_back([=](cudaStream_t s) { return launch_conv_tc(dp, d, s); });
+        BWD_PUSH([=](cudaStream_t s) { return launch_conv_tc(dp, d, s); });
       } else {
         const int planes = src->planes;
         void* dplanes = nullptr;
@@ -362,18 +362,18 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
           TcPlan* dp = nullptr;
           YB_PROPAGATE(tc_plan_create(d, B, &dp));
           t->plans.push_back(dp);
-          t->bwd.push_back([=](cudaStream_t s) { return launch_conv_tc(dp, d, s); });
+          BWD_PUSH([=](cudaStream_t s) { return launch_conv_tc(dp, d, s); });
         }
         const int Cin = c->Cin;
         if (!x->grad_set) {
           void* xg = x->grad;
-          t->bwd.push_back([=](cudaStream_t s) { return launch_phase_merge(dplanes, xg, dt, B, Cin, Hin, Hout, planes, plane_rows, s); });
+          BWD_PUSH([=](cudaStream_t s) { return launch_phase_merge(dplanes, xg, dt, B, Cin, Hin, Hout, planes, plane_rows, s); });
         } else {
           void* tmp = nullptr;
           YB_PROPAGATE(dev_alloc(t, &tmp, (size_t)x->rows * x->C * 2));
           void* xg = x->grad; const long long n = x->rows * x->C;
-          t->bwd.push_back([=](cudaStream_t s) { return launch_phase_merge(dplanes, tmp, dt, B, Cin, Hin, Hout, planes, plane_rows, s); });
-          t->bwd.push_back([=](cudaStream_t s) { return launch_add16(xg, tmp, dt, n, s); });
+          BWD_PUSH([=](cudaStream_t s) { return launch_phase_merge(dplanes, tmp, dt, B, Cin, Hin, Hout, planes, plane_rows, s); });
+          BWD_PUSH([=](cudaStream_t s) { return launch_add16(xg, tmp, dt, n, s); });
         }
       }
       x->grad_set = true;
@@ -387,6 +387,7 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
 // ---- batch-norm (+ residual, + ReLU) ----
 int op_bn(yb_train* t, TT* y, const std::string& bn, int relu, TT* res, const std::string& zname, TT** out) {
   const int B = t->B, C = y->C, H = y->H, dt = t->dt;
+  t->cur_label = "bn " + zname;
   for (const char* sfx : {".weight", ".bias"}) t->add_bound(bn + sfx, C, 0);
   for (const char* sfx : {".running_mean", ".running_var"}) t->add_bound(bn + sfx, C, 1);
   TT* z = new_tensor(t, zname, C, H);
@@ -398,15 +399,16 @@ int op_bn(yb_train* t, TT* y, const std::string& bn, int relu, TT* res, const st
   const double count = (double)B * H * H;
   const long long rows = y->rows;
   void* yd = y->data; void* zd = z->data; void* rd = res ? res->data : nullptr;
-  t->fwd.push_back([=](cudaStream_t s) { return launch_colstats(yd, dt, rows, C, (float*)((char*)t->stats + (size_t)sums), s); });
-  t->fwd.push_back([=](cudaStream_t s) {
+  FWD_PUSH([=](cudaStream_t s) { return launch_colstats(yd, dt, rows, C, (float*)((char*)t->stats + (size_t)sums), s); });
+  FWD_PUSH([=](cudaStream_t s) {
     return launch_bn_finalize((float*)((char*)t->stats + (size_t)sums), C, count, t->bound[ig].data, t->bound[ib].data, t->bound[im].data, t->bound[iv].data,
                               t->hp.bn_momentum, t->hp.bn_eps, aff, aff + C, aff + 2 * C, aff + 3 * C, s);
   });
-  t->fwd.push_back([=](cudaStream_t s) { return launch_bn_apply(yd, zd, rd, aff, aff + C, relu, dt, B, C, H, s); });
+  FWD_PUSH([=](cudaStream_t s) { return launch_bn_apply(yd, zd, rd, aff, aff + C, relu, dt, B, C, H, s); });
 
   float* bsums = stats_take(t, 2 * C);
   t->bwd_builders.push_back([=]() -> int {
+    t->cur_label = "bn-bwd " + z->name;
     YB_REQUIRE(z->grad != nullptr && z->grad_set, YB_ERR_STATE, "train: bn output %s has no gradient", z->name.c_str());
     YB_PROPAGATE(ensure_grad(t, y));
     void* dz = z->grad; void* dyp = y->grad;
@@ -416,16 +418,16 @@ int op_bn(yb_train* t, TT* y, const std::string& bn, int relu, TT* res, const st
       if (!res->grad_set) dres = res->grad;
       else { YB_PROPAGATE(dev_alloc(t, &tmp, (size_t)res->rows * res->C * 2)); dres = tmp; }
     }
-    t->bwd.push_back([=](cudaStream_t s) {
+    BWD_PUSH([=](cudaStream_t s) {
       return launch_bn_bwd_reduce(yd, dz, zd, relu, aff + 2 * C, aff + 3 * C, dt, rows, C, (float*)((char*)t->stats + (size_t)bsums), s);
     });
-    t->bwd.push_back([=](cudaStream_t s) {
+    BWD_PUSH([=](cudaStream_t s) {
       return launch_bn_bwd_apply(yd, dz, zd, relu, aff + 2 * C, aff + 3 * C, t->bound[ig].data, (float*)((char*)t->stats + (size_t)bsums), count, dyp, dres,
                                  t->bound[ig].grad, t->bound[ib].grad, 1.f, dt, B, C, H, s);
     });
     if (tmp) {
       void* rg = res->grad; const long long n = res->rows * res->C;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_add16(rg, tmp, dt, n, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_add16(rg, tmp, dt, n, s); });
     }
     if (res && res->needs_grad) res->grad_set = true;
     y->grad_set = true;
@@ -445,8 +447,8 @@ int build(yb_train* t) {
   // ---------------- stem: space-to-depth image -> 4-tap K=64 conv -> BN -> ReLU -> max-pool ----------------
   const int H1 = t->H1, Wp1 = H1 + 2;
   t->add_bound("backbone.conv1.weight", 64 * 3 * 7 * 7, 0);
-  TT* s2d = new_tensor(t, "stem.s2d", 16, H1);
-  YB_PROPAGATE(alloc_data(t, s2d, Wp1 + 4));
+  TT* s2d = new_tensor(t, "stem.s2d", 64, H1);            // 4 pixels x 16 channels per row (materialised: rows are self-contained)
+  YB_PROPAGATE(alloc_data(t, s2d));
   s2d->needs_grad = false;
   void* w16 = nullptr;
   YB_PROPAGATE(dev_alloc(t, &w16, 64 * 256 * 2));
@@ -454,39 +456,36 @@ int build(yb_train* t) {
   YB_PROPAGATE(alloc_data(t, sy));
   {
     void* s2dd = s2d->data; float* img = t->d_img;
-    t->fwd.push_back([=](cudaStream_t s) { return launch_stem_s2d(img, s2dd, dt, 0, B, S, H1, s); });
+    FWD_PUSH([=](cudaStream_t s) { return launch_stem_s2d(img, s2dd, dt, 1, B, S, H1, s); });
     const int iw = t->bidx.at("backbone.conv1.weight");
-    t->fwd.push_back([=](cudaStream_t s) { return launch_pack_stem(t->bound[iw].data, w16, dt, s); });
+    FWD_PUSH([=](cudaStream_t s) { return launch_pack_stem(t->bound[iw].data, w16, dt, s); });
     ConvArgs a; memset(&a, 0, sizeof(a));
     a.in = s2d->data; a.weight = w16; a.bias = t->zeros; a.out = sy->data; a.act_dt = dt; a.B = B; a.g.H = H1; a.g.W = H1;
     a.Cin = 64; a.Cin_pad = 64; a.Cout = 64; a.Cout_pad = 64; a.ntaps = 4; a.relu = 0; a.out_mode = 0;
     for (int dy = 0; dy < 4; ++dy) a.tap_shift[dy] = (dy - 1) * Wp1 - 1;
-    a.in_rows = s2d->rows; a.in_row_stride = 16;
-    YB_REQUIRE(tc_overlapping_rows_ok(), YB_ERR_UNSUPPORTED, "train: the driver refuses overlapping tensor-map rows (stem)");
+    a.in_rows = s2d->rows;
     TcPlan* pl = nullptr;
     YB_PROPAGATE(tc_plan_create(a, B, &pl));
     t->plans.push_back(pl);
-    t->fwd.push_back([=](cudaStream_t s) { return launch_conv_tc(pl, a, s); });
+    FWD_PUSH([=](cudaStream_t s) { return launch_conv_tc(pl, a, s); });
     // backward: weight gradient only (the image needs no gradient): 16 taps (dy, dx) of 16 channels each
     float* dW16 = nullptr;
     YB_PROPAGATE(dev_alloc(t, (void**)&dW16, 64 * 256 * 4));
     t->bwd_builders.push_back([=]() -> int {
       YB_REQUIRE(sy->grad && sy->grad_set, YB_ERR_STATE, "train: stem output has no gradient");
       const long long rows = sy->rows, ldT = (rows + 7) / 8 * 8;
-      void *dyT = nullptr, *xT = nullptr;
+      void* dyT = nullptr;
       YB_PROPAGATE(dev_alloc(t, &dyT, (size_t)64 * ldT * 2));
-      YB_PROPAGATE(dev_alloc(t, &xT, (size_t)16 * ldT * 2));
       void* dy = sy->grad;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_transpose16(dy, 64, dyT, dt, rows, 64, ldT, s); });
-      t->bwd.push_back([=](cudaStream_t s) { return launch_transpose16(s2dd, 16, xT, dt, rows, 16, ldT, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_transpose16(dy, 64, dyT, dt, rows, 64, ldT, s); });
       GemmArgs g; memset(&g, 0, sizeof(g));
-      g.a = dyT; g.b = xT; g.out = dW16; g.act_dt = dt; g.M = 64; g.Nper = 16; g.K = (int)rows; g.lda = (int)ldT; g.ldb = (int)ldT; g.Kb = rows; g.ntaps = 16;
-      for (int dy_ = 0; dy_ < 4; ++dy_) for (int dx = 0; dx < 4; ++dx) g.shift[dy_ * 4 + dx] = (dy_ - 1) * Wp1 - 1 + dx;
+      g.a = dyT; g.b = s2dd; g.out = dW16; g.act_dt = dt; g.M = 64; g.Nper = 64; g.K = (int)rows; g.lda = (int)ldT; g.ldb = 64; g.Kb = rows; g.ntaps = 4;
+      for (int dy_ = 0; dy_ < 4; ++dy_) g.shift[dy_] = (dy_ - 1) * Wp1 - 1;        // out [64][dy*64 + dx*16 + e]: the packed stem layout
       TcPlan* gp = nullptr;
       YB_PROPAGATE(tc_plan_create_gemm(g, &gp));
       t->plans.push_back(gp);
-      t->bwd.push_back([=](cudaStream_t s) { return launch_gemm_tc(gp, g, s); });
-      t->bwd.push_back([=](cudaStream_t s) { return launch_unpack_stem_grad(dW16, t->bound[iw].grad, 1.f, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_gemm_tc(gp, g, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_unpack_stem_grad(dW16, t->bound[iw].grad, 1.f, s); });
       return YB_OK;
     });
   }
@@ -496,13 +495,13 @@ int build(yb_train* t) {
   YB_PROPAGATE(alloc_data(t, x));
   {
     void* in = sz->data; void* out = x->data; const int H2 = t->H2;
-    t->fwd.push_back([=](cudaStream_t s) { return launch_maxpool(in, out, dt, B, 64, H1, H2, s); });
+    FWD_PUSH([=](cudaStream_t s) { return launch_maxpool(in, out, dt, B, 64, H1, H2, s); });
     TT* xx = x;
     t->bwd_builders.push_back([=]() -> int {
       YB_REQUIRE(xx->grad && xx->grad_set, YB_ERR_STATE, "train: pool output has no gradient");
       YB_PROPAGATE(ensure_grad(t, sz));
       void* dy = xx->grad; void* dx = sz->grad;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_maxpool_bwd(in, dy, dx, dt, B, 64, H1, H2, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_maxpool_bwd(in, dy, dx, dt, B, 64, H1, H2, s); });
       sz->grad_set = true;
       return YB_OK;
     });
@@ -564,12 +563,12 @@ int build(yb_train* t) {
   for (int i = 0; i < 2; ++i) YB_PROPAGATE(biased("fpn.downsample_layers." + std::to_string(i) + ".0", 256, 256, 3, 2, &down[i]));
   auto upadd = [&](TT* coarse, TT* fine) {
     void* cd = coarse->data; void* fd = fine->data; const int Hc = coarse->H, Hf = fine->H;
-    t->fwd.push_back([=](cudaStream_t s) { return launch_upsample_add(cd, fd, dt, B, 256, Hc, Hf, s); });
+    FWD_PUSH([=](cudaStream_t s) { return launch_upsample_add(cd, fd, dt, B, 256, Hc, Hf, s); });
     t->bwd_builders.push_back([=]() -> int {
       YB_REQUIRE(fine->grad && fine->grad_set, YB_ERR_STATE, "train: FPN level %s has no gradient", fine->name.c_str());
       YB_PROPAGATE(ensure_grad(t, coarse));
       void* df = fine->grad; void* dc = coarse->grad; const int acc = coarse->grad_set ? 1 : 0;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_bilinear_bwd(df, dc, dt, B, 256, Hc, Hf, 0, acc, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_bilinear_bwd(df, dc, dt, B, 256, Hc, Hf, 0, acc, s); });
       coarse->grad_set = true;
       return YB_OK;
     });
@@ -599,12 +598,12 @@ int build(yb_train* t) {
   YB_PROPAGATE(alloc_data(t, up));
   {
     void* in = q->data; void* out = up->data; const int Hin = q->H; TT* qq = q;
-    t->fwd.push_back([=](cudaStream_t s) { return launch_upsample2x_ac(in, out, dt, B, 256, Hin, s); });
+    FWD_PUSH([=](cudaStream_t s) { return launch_upsample2x_ac(in, out, dt, B, 256, Hin, s); });
     t->bwd_builders.push_back([=]() -> int {
       YB_REQUIRE(up->grad && up->grad_set, YB_ERR_STATE, "train: proto up-sample has no gradient");
       YB_PROPAGATE(ensure_grad(t, qq));
       void* df = up->grad; void* dc = qq->grad; const int acc = qq->grad_set ? 1 : 0;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_bilinear_bwd(df, dc, dt, B, 256, Hin, 2 * Hin, 1, acc, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_bilinear_bwd(df, dc, dt, B, 256, Hin, 2 * Hin, 1, acc, s); });
       qq->grad_set = true;
       return YB_OK;
     });
@@ -640,7 +639,7 @@ int build(yb_train* t) {
     for (const auto& n : hc->cat) {
       const int ib = t->bidx.at(n + ".bias"), cnt = (int)t->bound[ib].count;
       float* dst = hc->bias_cat + row;
-      t->fwd.push_back([=](cudaStream_t s) { return launch_scale_copy(t->bound[ib].data, dst, cnt, 1.f, s); });
+      FWD_PUSH([=](cudaStream_t s) { return launch_scale_copy(t->bound[ib].data, dst, cnt, 1.f, s); });
       row += cnt;
     }
   }
@@ -659,13 +658,13 @@ int build(yb_train* t) {
     {
       const float* hd = (const float*)h->data; const int ld = hc->Cout_pad, HW = lv[l]->H * lv[l]->H, aoff = t->level_off[l], A = t->A, Hl = lv[l]->H;
       float *cls = t->cls, *box = t->box, *coef = t->coef;
-      t->fwd.push_back([=](cudaStream_t s) { return launch_head_train(hd, ld, B, HW, R, NC, K, aoff, A, cls, box, coef, s); });
+      FWD_PUSH([=](cudaStream_t s) { return launch_head_train(hd, ld, B, HW, R, NC, K, aoff, A, cls, box, coef, s); });
       TT* hh = h;
       t->bwd_builders.push_back([=]() -> int {
         YB_PROPAGATE(ensure_grad(t, hh));
         void* g = hh->grad; const int ldo = hh->Cg;
         float *gc = t->g_cls, *gb = t->g_box, *gk = t->g_coef;
-        t->bwd.push_back([=](cudaStream_t s) { return launch_head_grad(gc, gb, gk, coef, dt, B, Hl, R, NC, K, aoff, A, ldo, g, s); });
+        BWD_PUSH([=](cudaStream_t s) { return launch_head_grad(gc, gb, gk, coef, dt, B, Hl, R, NC, K, aoff, A, ldo, g, s); });
         hh->grad_set = true;
         return YB_OK;
       });
@@ -683,8 +682,8 @@ int build(yb_train* t) {
       YB_PROPAGATE(ensure_grad(t, ss)); YB_PROPAGATE(ensure_grad(t, pp));
       void* gs = ss->grad; void* gp = pp->grad; const int Cs = ss->Cg, Cp = pp->Cg, Hs = t->Hs, P = t->P, lds = t->ld_seg;
       float *dseg = t->g_seg, *dproto = t->g_proto, *proto = t->proto;
-      t->bwd.push_back([=](cudaStream_t s) { return launch_dense_to_haloed(dseg, nullptr, lds, NC - 1, gs, dt, B, Cs, Hs, s); });
-      t->bwd.push_back([=](cudaStream_t s) { return launch_dense_to_haloed(dproto, proto, K, K, gp, dt, B, Cp, P, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_dense_to_haloed(dseg, nullptr, lds, NC - 1, gs, dt, B, Cs, Hs, s); });
+      BWD_PUSH([=](cudaStream_t s) { return launch_dense_to_haloed(dproto, proto, K, K, gp, dt, B, Cp, P, s); });
       ss->grad_set = true; pp->grad_set = true;
       return YB_OK;
     });
@@ -845,8 +844,14 @@ extern "C" int yb_train_forward(yb_train* t, const float* img, const float* gt, 
   YB_CHECK_CUDA(cudaMemcpyAsync(t->d_img, img, (size_t)t->B * 3 * t->S * t->S * 4, cudaMemcpyDeviceToDevice, s));
   YB_CHECK_CUDA(cudaMemsetAsync(t->stats, 0, t->stats_floats * 4, s));
   YB_PROPAGATE(launch_pack_weights(t->d_pack, (int)t->pack_descs.size(), t->dt, s));
-  for (auto& f : t->fwd) YB_PROPAGATE(f(s));
+  static const bool dbg = getenv("YOLACT_B200_TRAIN_DEBUG") != nullptr;
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: before the forward list: %s", cudaGetErrorString(e)); }
+  for (size_t i = 0; i < t->fwd.size(); ++i) {
+    YB_PROPAGATE(t->fwd[i](s));
+    if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: forward launch %zu (%s): %s", i, t->fwd_what[i].c_str(), cudaGetErrorString(e)); }
+  }
   YB_PROPAGATE(run_losses(t, false, s));
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: losses: %s", cudaGetErrorString(e)); }
   t->launches_fwd = yb_launch_count() - l0;
   return YB_OK;
 }
@@ -858,9 +863,15 @@ extern "C" int yb_train_backward(yb_train* t, const float* loss_grad, void* stre
   t->loss_grad = loss_grad;
   const uint64_t l0 = yb_launch_count();
   YB_CHECK_CUDA(cudaMemsetAsync(t->stats, 0, t->stats_floats * 4, s));    // BN reductions / bias sums of this pass start from zero
+  static const bool dbg = getenv("YOLACT_B200_TRAIN_DEBUG") != nullptr;
   YB_PROPAGATE(run_losses(t, true, s));
-  for (auto& f : t->bwd) YB_PROPAGATE(f(s));
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: loss gradients: %s", cudaGetErrorString(e)); }
+  for (size_t i = 0; i < t->bwd.size(); ++i) {
+    YB_PROPAGATE(t->bwd[i](s));
+    if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: backward launch %zu (%s): %s", i, t->bwd_what[i].c_str(), cudaGetErrorString(e)); }
+  }
   for (auto& f : t->bwd_tail) YB_PROPAGATE(f(s));
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: backward tail: %s", cudaGetErrorString(e)); }
   YB_PROPAGATE(launch_unpack_wgrad(t->d_unpack, (int)t->unpack_descs.size(), s));
   t->launches_bwd = yb_launch_count() - l0;
   return YB_OK;

@@ -122,6 +122,7 @@ class _NativeTrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, img, gt, gt_off, masks, total_gt, max_gt, seed, *params):
         ctx.eng = eng
+        ctx.keep = (gt, gt_off, masks)                 # the backward pass re-reads the targets through the engine's raw pointers
         return eng.forward(img, gt, gt_off, masks, total_gt, max_gt, seed)
 
     @staticmethod

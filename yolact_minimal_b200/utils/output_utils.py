@@ -17,10 +17,10 @@ _ws_cache = {}
 _anchor_cache = {}
 
 
-def _params(cfg, num_classes, coef_dim):
+def _params(cfg, num_classes, coef_dim, no_clip=False):
     return _lib.DetectParams(float(cfg.nms_score_thre), float(cfg.nms_iou_thre), int(cfg.top_k),
                              int(cfg.max_detections), int(num_classes), int(coef_dim),
-                             1 if getattr(cfg, 'traditional_nms', False) else 0, float(getattr(cfg, 'img_size', 0)))
+                             1 if getattr(cfg, 'traditional_nms', False) else 0, float(getattr(cfg, 'img_size', 0)), 1 if no_clip else 0)
 
 
 def _workspace(nbytes, device):
@@ -74,7 +74,7 @@ def record_views(flat, B, D, K):
     return out
 
 
-def detect_batched(class_pred, box_pred, coef_pred, anchors, cfg):
+def detect_batched(class_pred, box_pred, coef_pred, anchors, cfg, no_clip=False):
     """Batched decode + (Fast|traditional) NMS + top-k.
     class_pred [B,A,C] (post-softmax), box_pred [B,A,4], coef_pred [B,A,K].
     Returns dict of padded tensors: count [B] int32, class [B,D] int32, anchor [B,D] int32,
@@ -91,7 +91,7 @@ def detect_batched(class_pred, box_pred, coef_pred, anchors, cfg):
     anc = _device_anchors(anchors, dev)
     if anc.shape[0] != A:
         raise ValueError(f'anchors has {anc.shape[0]} rows, predictions have {A}')
-    p = _params(cfg, C, K)
+    p = _params(cfg, C, K, no_clip)
     D = p.max_det
     L = _lib.lib()
     # ONE flat int32 buffer [count B | class B*D | anchor B*D | score B*D | box B*D*4 | coef B*D*K]; the dict entries are typed views
@@ -126,7 +126,8 @@ def after_nms(ids_p, class_p, box_p, coef_p, proto_p, img_h, img_w, cfg=None, im
     """Reference signature (utils/output_utils.py:200).  Returns (ids, scores, boxes int32 [d,4]
     in pixels of max(img_h,img_w), masks [d,img_h,img_w] with values {0,1}) or (None,)*4.
     `mask_dtype=torch.uint8` writes byte masks instead of the reference's float32 (4x less HBM
-    traffic); unlike the reference, box_p is not modified in place."""
+    traffic), `mask_dtype='bits'` bit-packed masks [d,img_h,ceil(img_w/32)] (32x less; utils/mask_utils.py has
+    the IoU / RLE stage that consumes them); unlike the reference, box_p is not modified in place."""
     if ids_p is None:
         return None, None, None, None
     _require_cuda(box_p, coef_p, proto_p)
@@ -147,12 +148,76 @@ def after_nms(ids_p, class_p, box_p, coef_p, proto_p, img_h, img_w, cfg=None, im
         raise ValueError(f'proto {tuple(proto.shape)} does not match coef {tuple(coef.shape)}')
     crop = 0 if (cfg is not None and getattr(cfg, 'no_crop', False)) else 1
     f32 = mask_dtype == torch.float32
-    masks = torch.empty(d, int(img_h), int(img_w), dtype=torch.float32 if f32 else torch.uint8, device=dev)
+    fmt = 2 if isinstance(mask_dtype, str) and mask_dtype == 'bits' else (1 if f32 else 0)
+    if fmt == 2:
+        masks = torch.empty(d, int(img_h), (int(img_w) + 31) // 32, dtype=torch.int32, device=dev)
+    else:
+        masks = torch.empty(d, int(img_h), int(img_w), dtype=torch.float32 if f32 else torch.uint8, device=dev)
     boxes_px = torch.empty(d, 4, dtype=torch.int32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
         ws = torch.empty(int(L.yb_mask_workspace_bytes(d, P)), dtype=torch.uint8, device=dev)
         _lib.check(L.yb_mask_assemble(proto.data_ptr(), coef.data_ptr(), box.data_ptr(), d, P, K, int(img_h), int(img_w),
-                                      crop, 1 if f32 else 0, ws.data_ptr(), ws.numel(), masks.data_ptr(),
+                                      crop, fmt, ws.data_ptr(), ws.numel(), masks.data_ptr(),
                                       boxes_px.data_ptr(), torch.cuda.current_stream().cuda_stream), 'yb_mask_assemble')
     return ids_p, class_p, boxes_px, masks
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The ONNX / TensorRT callers' numpy twins (utils/output_utils.py:46-81,:166-197,:236-273; detect_with_onnx.py, detect_with_trt.py):
+# numpy arrays in, numpy arrays out, same return conventions -- computed by the same CUDA kernels.  Semantics kept from the
+# reference: NO clip of the decoded boxes to [0,1] (compare :186-190 with :153) and boolean masks.  Two documented differences:
+# the reference decodes in float64 (its anchors are a float64 array) and resizes the masks with cv2.INTER_LINEAR; here the decode
+# is the fp32 kernel and the resize the same half-pixel bilinear kernel as after_nms (boxes agree to ~1e-6, masks to a few pixels
+# on the contour).
+# ---------------------------------------------------------------------------------------------------------------------------
+def _np_dev():
+    if not torch.cuda.is_available():
+        raise _lib.YolactB200Error('the numpy post-process twins run on a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def nms_numpy(class_pred, box_pred, coef_pred, proto_out, anchors, cfg):
+    """utils/output_utils.py:166-197.  Returns (class_ids, class_thre, box_thre, coef_thre, proto_p) as numpy arrays or (None,)*5."""
+    import numpy as np
+    assert not getattr(cfg, 'traditional_nms', False), 'Traditional nms is not supported with numpy.'          # :193
+    dev = _np_dev()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(dev)
+    cls, box, coef = t(np.squeeze(class_pred)), t(np.squeeze(box_pred)), t(np.squeeze(coef_pred))
+    proto = np.squeeze(np.asarray(proto_out))
+    anc = t(np.asarray(anchors, dtype=np.float64).reshape(-1, 4))
+    r = detect_batched(cls[None], box[None], coef[None], anc, cfg, no_clip=True)
+    d = int(r['count'][0].item())
+    if d == 0:
+        return None, None, None, None, None
+    return (r['cls'][0, :d].cpu().numpy().astype(np.int64), r['score'][0, :d].cpu().numpy(), r['box'][0, :d].cpu().numpy(),
+            r['coef'][0, :d].cpu().numpy(), proto)
+
+
+def after_nms_numpy(ids_p, class_p, box_p, coef_p, proto_p, img_h, img_w, cfg=None):
+    """utils/output_utils.py:236-273.  Returns (ids, scores, boxes int32 [d,4], masks bool [d,img_h,img_w]) or (None,)*4."""
+    import numpy as np
+    if ids_p is None:
+        return None, None, None, None
+    if cfg and getattr(cfg, 'visual_thre', 0) > 0:
+        keep = class_p >= cfg.visual_thre
+        if not keep.any():
+            return None, None, None, None
+        ids_p, class_p, box_p, coef_p = ids_p[keep], class_p[keep], box_p[keep], coef_p[keep]
+    assert not (cfg and getattr(cfg, 'save_lincomb', False)), 'save_lincomb is not supported in onnx mode.'   # :253
+    dev = _np_dev()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(dev)
+    r = after_nms(ids_p, class_p, t(box_p), t(coef_p), t(proto_p), img_h, img_w, cfg=None if cfg is None else _NoVisual(cfg), mask_dtype=torch.uint8)
+    return ids_p, class_p, r[2].cpu().numpy().astype(np.int32), r[3].cpu().numpy().astype(bool)
+
+
+class _NoVisual:
+    """cfg view for after_nms_numpy: the score filter was already applied on the numpy side."""
+
+    def __init__(self, cfg):
+        self._cfg = cfg
+
+    def __getattr__(self, k):
+        if k == 'visual_thre':
+            return 0
+        return getattr(self._cfg, k)
