@@ -5,11 +5,14 @@
 // (__f*_rn, no FMA contraction) in the reference's order -- see DESIGN.md "index exactness".
 //
 // Data flow (per image b, A anchors, C classes incl. background, C1 = C-1):
+//   phase 0  k_sample_cuts     grid (8, B): per-class score cuts from 1024 sampled anchors (Fast-NMS only)
 //   phase 1  k_filter_decode   grid (ceil(A/128), B): streams cls[b] once (coalesced, the only
 //            HBM-heavy step: A*C*4 bytes), keeps anchors whose fg max > thr, decodes their
-//            boxes, and writes a compacted, class-major (transposed) score matrix
-//            scoreT[b][c][slot] so that phase 2 reads rows, not 81-float strided columns.
-//   phase 2  k_class_fast_nms  grid (C1, B): radix-select the top_k scores of the class row,
+//            boxes, and appends every (candidate, class) score that reaches the class's cut to the
+//            class's candidate list (Fast-NMS; ~3 top_k entries per class instead of the whole
+//            [C1][n] transposed score matrix of round 1, which cost 2.6x the algorithmic DRAM
+//            traffic), or writes the transposed matrix scoreT[b][c][slot] (traditional NMS).
+//   phase 2  k_class_fast_nms  grid (C1, B): radix-select the top_k scores of the class's list,
 //            bitonic-sort them (score desc, anchor asc), k x k IoU upper triangle, keep rule.
 //            (k_class_hard_nms is the traditional_nms alternative.)
 //   phase 3  k_final_topk      grid (B): select max_det best of the <= C1*max_det survivors,
@@ -23,6 +26,9 @@ constexpr int kP1Anchors = 128;   // anchors per phase-1 tile
 constexpr int kThreads = 256;
 constexpr int kSortCap = 256;     // top_k, max_det <= 256
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kListCap = 4096;   // entries per (image, class) candidate list == the compact capacity of the per-class kernel
+constexpr int kBins = 116;        // sampled-score histogram: 8 bins per binary exponent over [2^-14, 1), + underflow / overflow
+constexpr int kSamples = 1024, kSampleBlocks = 8;
 
 struct DetectWs {
   int* cand_count;    // [B]
@@ -34,20 +40,31 @@ struct DetectWs {
   int* cls_anchor;    // [B][C1][KC]
   int* cls_slot;      // [B][C1][KC]
   int KC;
+  // Fast-NMS path: per-class candidate lists instead of the transposed score matrix
+  uint32_t* cut;      // [B][C1]   ordered-key threshold below which a class score cannot reach the class's top_k (0 = take all)
+  int* list_cnt;      // [B][C1]   entries appended (may exceed kListCap: the list overflowed -> exact fallback)
+  uint2* list;        // [B][C1][kListCap]  (ordered score key, candidate slot)
+  int* hist;          // [B][C1][kBins]     sampled score histogram
+  int* samp;          // [B][2]    sampled candidate count, finished sample blocks
 };
 
-static size_t carve(DetectWs* w, char* base, int B, int A, int C1, int KC) {
+static size_t carve(DetectWs* w, char* base, int B, int A, int C1, int KC, bool traditional) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? base + o : (char*)nullptr; };
   w->cand_count = (int*)take(sizeof(int) * B);
   w->cand_anchor = (int*)take(sizeof(int) * (size_t)B * A);
   w->cand_box = (float4*)take(sizeof(float4) * (size_t)B * A);
-  w->scoreT = (float*)take(sizeof(float) * (size_t)B * C1 * A);
+  w->scoreT = (float*)take(traditional ? sizeof(float) * (size_t)B * C1 * A : 16);
   w->cls_cnt = (int*)take(sizeof(int) * (size_t)B * C1);
   w->cls_score = (float*)take(sizeof(float) * (size_t)B * C1 * KC);
   w->cls_anchor = (int*)take(sizeof(int) * (size_t)B * C1 * KC);
   w->cls_slot = (int*)take(sizeof(int) * (size_t)B * C1 * KC);
   w->KC = KC;
+  w->cut = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * C1);
+  w->list_cnt = (int*)take(sizeof(int) * (size_t)B * C1);
+  w->list = (uint2*)take(traditional ? 16 : sizeof(uint2) * (size_t)B * C1 * kListCap);
+  w->hist = (int*)take(traditional ? 16 : sizeof(int) * (size_t)B * C1 * kBins);
+  w->samp = (int*)take(sizeof(int) * (size_t)B * 2);
   return off;
 }
 
@@ -100,8 +117,82 @@ __device__ __forceinline__ float ovr_plus1(float4 a, float area_a, float4 b, flo
 }
 
 // --------------------------------------------------------------------------------------------
-// phase 1: filter + decode + transpose
+// phase 0 (Fast-NMS): per-class score cuts from a sample of the image's anchors.
+// Only the top_k scores of a class row can matter (output_utils.py:12-14), so phase 1 appends an (anchor, class) score to the
+// class's candidate list only if it is >= a per-class cut -- instead of materialising the whole [C1][n] transposed score matrix
+// (2.6x the algorithmic DRAM traffic in round 1).  The cut comes from kSamples strided anchors: candidate samples are histogrammed
+// per class over ~12 % wide score bins; the cut is the lower edge of the bin where the sampled rank reaches ~3 top_k * (samples /
+// anchors).  Exactness does not depend on the estimate: the per-class kernel takes the list only if it holds >= top_k entries and
+// did not overflow (then the true top_k are all in it), otherwise it selects over the class column of `cls` itself.
 // --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int score_bin(float f) {
+  if (!(f >= 6.103515625e-05f)) return 0;                 // < 2^-14, negative or NaN
+  if (f >= 1.f) return kBins - 1;
+  const uint32_t u = __float_as_uint(f);
+  const int e = (int)(u >> 23) - 127;                     // -14 .. -1
+  return 1 + (e + 14) * 8 + (int)((u >> 20) & 7u);
+}
+__device__ __forceinline__ float bin_lower_edge(int bin) {
+  if (bin <= 0) return 0.f;
+  if (bin >= kBins - 1) return 1.f;
+  const int q = bin - 1, e = q / 8 - 14, m = q & 7;
+  return __uint_as_float(((uint32_t)(e + 127) << 23) | ((uint32_t)m << 20));
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_sample_cuts(const float* __restrict__ cls, int A, int C, float score_thr, int top_k, DetectWs ws) {
+  extern __shared__ int s_hist[];                         // [C1][kBins]
+  __shared__ int s_cnt, s_last;
+  const int b = blockIdx.y, tid = threadIdx.x, C1 = C - 1;
+  const int per_block = kSamples / kSampleBlocks;         // 128 samples, two threads each
+  for (int i = tid; i < C1 * kBins; i += kThreads) s_hist[i] = 0;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  const int la = tid >> 1, half = tid & 1;
+  const int si = blockIdx.x * per_block + la;             // sample index
+  const long long a = ((long long)si * A) / kSamples;     // strided anchors
+  const float* row = cls + ((size_t)b * A + (size_t)a) * C;
+  float m = -INFINITY; bool has_nan = false;
+  for (int c = 1 + half; c < C; c += 2) { const float v = __ldg(row + c); has_nan |= (v != v); m = v > m ? v : m; }
+  const float mo = __shfl_xor_sync(kFull, m, 1);
+  const bool no = __shfl_xor_sync(kFull, (int)has_nan, 1) != 0;
+  m = mo > m ? mo : m; has_nan |= no;
+  const bool cand = !has_nan && m > score_thr;
+  if (cand) {
+    if (half == 0) atomicAdd(&s_cnt, 1);
+    for (int c = 1 + half; c < C; c += 2) atomicAdd(&s_hist[(c - 1) * kBins + score_bin(__ldg(row + c))], 1);
+  }
+  __syncthreads();
+  int* gh = ws.hist + (size_t)b * C1 * kBins;
+  for (int i = tid; i < C1 * kBins; i += kThreads) { const int v = s_hist[i]; if (v) atomicAdd(&gh[i], v); }
+  if (tid == 0 && s_cnt) atomicAdd(&ws.samp[b * 2], s_cnt);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&ws.samp[b * 2 + 1], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last block of the image turns the histogram into cuts
+  const int cnt = atomicAdd(&ws.samp[b * 2], 0);
+  const double est_n = (double)cnt * A / kSamples;        // estimated number of candidates of the image
+  for (int c = tid; c < C1; c += kThreads) {
+    uint32_t cut = 0u;
+    if (est_n > 0.6 * kListCap) {                         // otherwise every candidate fits the list: take all
+      const int want = (int)(3.0 * top_k * kSamples / A) + 8;      // sampled rank of ~3 top_k survivors, + margin
+      int acc = 0;
+      for (int bin = kBins - 1; bin > 0; --bin) {
+        acc += atomicAdd(&gh[c * kBins + bin], 0);
+        if (acc >= want) { cut = float_to_ordered(bin_lower_edge(bin)); break; }
+      }
+    }
+    ws.cut[(size_t)b * C1 + c] = cut;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// phase 1: filter + decode + (traditional: transpose | Fast-NMS: per-class candidate lists)
+// --------------------------------------------------------------------------------------------
+template <bool LISTS>
 __global__ void __launch_bounds__(kThreads)
 k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, const float* __restrict__ anchors,
                 int A, int C, float score_thr, int no_clip, DetectWs ws) {
@@ -163,11 +254,41 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
     ws.cand_box[slot] = decode_box(bb, an, no_clip);
   }
   __syncthreads();
-  // class-major write: warp w takes classes w, w+8, ...; lanes run over the kept anchors
-  float* dst = ws.scoreT + (size_t)b * C1 * A + base;
+  if (!LISTS) {
+    // class-major write: warp w takes classes w, w+8, ...; lanes run over the kept anchors
+    float* dst = ws.scoreT + (size_t)b * C1 * A + base;
+    for (int c = w; c < C1; c += kThreads / 32) {
+      float* drow = dst + (size_t)c * A;
+      for (int j = lane; j < total; j += 32) drow[j] = tile[s_kept[j] * C + c + 1];
+    }
+    return;
+  }
+  // per-class candidate lists: warp w takes classes w, w+8, ...; an entry is appended iff its score key reaches the class's cut
   for (int c = w; c < C1; c += kThreads / 32) {
-    float* drow = dst + (size_t)c * A;
-    for (int j = lane; j < total; j += 32) drow[j] = tile[s_kept[j] * C + c + 1];
+    const uint32_t cut = ws.cut[(size_t)b * C1 + c];
+    int cnt = 0;
+    for (int j0 = 0; j0 < total; j0 += 32) {
+      const int j = j0 + lane;
+      const bool take = j < total && float_to_ordered(tile[s_kept[j] * C + c + 1]) >= cut;
+      cnt += __popc(__ballot_sync(kFull, take));
+    }
+    if (cnt == 0) continue;                                            // warp-uniform
+    int lbase = 0;
+    if (lane == 0) lbase = atomicAdd(&ws.list_cnt[(size_t)b * C1 + c], cnt);
+    lbase = __shfl_sync(kFull, lbase, 0);
+    uint2* dst = ws.list + ((size_t)b * C1 + c) * kListCap;
+    for (int j0 = 0; j0 < total; j0 += 32) {
+      const int j = j0 + lane;
+      uint32_t key = 0u;
+      bool take = false;
+      if (j < total) { key = float_to_ordered(tile[s_kept[j] * C + c + 1]); take = key >= cut; }
+      const unsigned bal = __ballot_sync(kFull, take);
+      if (take) {
+        const int pos = lbase + __popc(bal & ((1u << lane) - 1u));
+        if (pos < kListCap) dst[pos] = make_uint2(key, (uint32_t)(base + j));
+      }
+      lbase += __popc(bal);
+    }
   }
 }
 
@@ -242,11 +363,9 @@ __device__ void bitonic_sort_256(unsigned long long* key, int* val) {
 
 // --------------------------------------------------------------------------------------------
 // phase 2 (Fast-NMS): one block per (class, image)   utils/output_utils.py:11-31
-//   stage 1  cut the class row (up to A scores) down to a compact candidate list in shared memory:
-//            a 256-element sample is sorted, its j-th largest value is a threshold that keeps
-//            ~4*top_k elements in expectation; one streaming pass compacts the survivors
-//            (ballot + one shared atomic per warp).  If fewer than top_k or more than kCompactCap
-//            survive (probability < 1e-3) the exact selection simply runs over the whole row.
+//   stage 1  load the class's candidate list written by phase 1 (every candidate whose class score reaches the sampled cut,
+//            phase 0) into shared memory; if the list cannot be trusted to hold the class's top_k (fewer than top_k entries,
+//            or it overflowed kListCap) the exact selection runs over the class column of `cls` instead (rare)
 //   stage 2  exact top_k of the compact list: 8-bit radix select, tie-break on anchor index,
 //            bitonic sort of the <= 256 winners by (score desc, anchor asc)
 //   stage 3  k x k IoU upper triangle, keep rule, ordered compaction of the survivors
@@ -286,10 +405,9 @@ __device__ __forceinline__ bool iou_le(float4 a, float area_a, float4 b, float a
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_class_fast_nms(int A, int C1, int top_k, float iou_thr, DetectWs ws) {
+k_class_fast_nms(const float* __restrict__ cls, int A, int C1, int top_k, float iou_thr, DetectWs ws) {
   __shared__ uint32_t s_ckey[kCompactCap];         // compact candidates: ordered score keys
   __shared__ int s_cidx[kCompactCap];              //                    : slot in the candidate list
-  __shared__ uint32_t s_sample[256];
   __shared__ unsigned long long s_sort[kSortCap];
   __shared__ int s_slot[kSortCap];
   __shared__ float4 s_box[kSortCap];
@@ -305,48 +423,20 @@ k_class_fast_nms(int A, int C1, int top_k, float iou_thr, DetectWs ws) {
   int* out_cnt = ws.cls_cnt + (size_t)b * C1 + c;
   if (n == 0) { if (tid == 0) *out_cnt = 0; return; }
   const int k = min(top_k, n);
-  const float* row = ws.scoreT + ((size_t)b * C1 + c) * A;
   const int* canchor = ws.cand_anchor + (size_t)b * A;
   if (tid == 0) { s_cnt = 0; s_m = 0; }
 
-  // ---- stage 1: compact candidate list ---------------------------------------------------------
-  bool full_scan = false;                          // exact selection over the whole row (rare)
-  int m = n;
-  if (n <= kCompactCap) {
-    for (int i = tid; i < n; i += kThreads) { s_ckey[i] = float_to_ordered(row[i]); s_cidx[i] = i; }
-    __syncthreads();
-  } else {
-    const int stride = n / 256;
-    s_sample[tid] = float_to_ordered(row[tid * stride]);
-    bitonic_sort_256_desc_u32(s_sample);
-    int j = (int)(((long long)256 * 4 * k + n - 1) / n) + 4;        // expected survivors ~ 4k + 4n/256
-    if (j > 255) j = 255;
-    const uint32_t cut = s_sample[j];
-    // 4 independent loads in flight per thread, then 4 ballot/append rounds
-    for (int i0 = 0; i0 < n; i0 += 4 * kThreads) {
-      uint32_t key[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int i = i0 + u * kThreads + tid; key[u] = i < n ? float_to_ordered(__ldg(row + i)) : 0u; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kThreads + tid;
-        const bool take = i < n && key[u] >= cut;
-        const unsigned bal = __ballot_sync(kFull, take);
-        if (bal == 0u) continue;                                   // warp-uniform
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
-        base = __shfl_sync(kFull, base, 0);
-        if (take) {
-          const int pos = base + __popc(bal & ((1u << lane) - 1u));
-          if (pos < kCompactCap) { s_ckey[pos] = key[u]; s_cidx[pos] = i; }
-        }
-      }
-    }
-    __syncthreads();
-    m = s_m;
-    if (m < k || m > kCompactCap) { full_scan = true; m = n; }
+  // ---- stage 1: the class's candidate list (phase 1), or -- when the list cannot hold the top_k for sure -- the class column ----
+  const int lcnt = ws.list_cnt[(size_t)b * C1 + c];
+  const bool full_scan = lcnt < k || lcnt > kListCap;      // cut too high / list overflowed (rare): exact selection over all candidates
+  int m = full_scan ? n : lcnt;
+  if (!full_scan) {
+    const uint2* lst = ws.list + ((size_t)b * C1 + c) * kListCap;
+    for (int i = tid; i < m; i += kThreads) { const uint2 e = lst[i]; s_ckey[i] = e.x; s_cidx[i] = (int)e.y; }
   }
-  auto key_of = [&](int i) -> uint32_t { return full_scan ? float_to_ordered(row[i]) : s_ckey[i]; };
+  __syncthreads();
+  const float* col = cls + (size_t)b * A * (C1 + 1) + c + 1;
+  auto key_of = [&](int i) -> uint32_t { return full_scan ? float_to_ordered(__ldg(col + (size_t)canchor[i] * (C1 + 1))) : s_ckey[i]; };
   auto slot_of = [&](int i) -> int { return full_scan ? i : s_cidx[i]; };
 
   // ---- stage 2: exact top-k by (score desc, anchor asc) ----------------------------------------
@@ -675,7 +765,7 @@ static int check_params(const yb_detect_params* p, int batch, int A) {
 extern "C" size_t yb_detect_workspace_bytes(int batch, int num_anchors, const yb_detect_params* p) {
   if (!p || batch <= 0 || num_anchors <= 0) return 0;
   DetectWs w;
-  return carve(&w, nullptr, batch, num_anchors, p->num_classes - 1, p->top_k > p->max_det ? p->top_k : p->max_det);
+  return carve(&w, nullptr, batch, num_anchors, p->num_classes - 1, p->top_k > p->max_det ? p->top_k : p->max_det, p->traditional != 0);
 }
 
 extern "C" int yb_detect(const float* cls, const float* box, const float* coef, const float* anchors,
@@ -690,20 +780,35 @@ extern "C" int yb_detect(const float* cls, const float* box, const float* coef, 
   const int B = batch, A = num_anchors, C = p->num_classes, C1 = C - 1;
   const int KC = p->top_k > p->max_det ? p->top_k : p->max_det;
   DetectWs ws;
-  const size_t need = carve(&ws, (char*)workspace, B, A, C1, KC);
+  const size_t need = carve(&ws, (char*)workspace, B, A, C1, KC, p->traditional != 0);
   YB_REQUIRE(workspace_bytes >= need, YB_ERR_INVALID, "yb_detect: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t stream = (cudaStream_t)stream_;
 
   YB_CHECK_CUDA(cudaMemsetAsync(ws.cand_count, 0, sizeof(int) * B, stream));
   {
     const size_t smem = (size_t)kP1Anchors * C * sizeof(float);
-    YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(A, kP1Anchors), B);
-    k_filter_decode<<<grid, kThreads, smem, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
+    if (p->traditional) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_filter_decode<false><<<grid, kThreads, smem, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
+    } else {
+      // cut [B][C1] | list_cnt [B][C1] are adjacent 256-byte aligned blocks: zero them (cut 0 = take all) and the sample state
+      YB_CHECK_CUDA(cudaMemsetAsync(ws.cut, 0, (size_t)((char*)ws.list - (char*)ws.cut), stream));
+      YB_CHECK_CUDA(cudaMemsetAsync(ws.samp, 0, sizeof(int) * (size_t)B * 2, stream));
+      if (A > kListCap) {                                     // small heads: every candidate fits its list, no sampling
+        YB_CHECK_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(int) * (size_t)B * C1 * kBins, stream));
+        const size_t hs = (size_t)C1 * kBins * sizeof(int);
+        YB_CHECK_CUDA(cudaFuncSetAttribute(k_sample_cuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+        k_sample_cuts<<<dim3(kSampleBlocks, B), kThreads, hs, stream>>>(cls, A, C, p->score_thr, p->top_k, ws);
+        YB_CHECK_LAUNCH();
+      }
+      YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_filter_decode<true><<<grid, kThreads, smem, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
+    }
     YB_CHECK_LAUNCH();
   }
   if (!p->traditional) {
-    k_class_fast_nms<<<dim3(C1, B), kThreads, 0, stream>>>(A, C1, p->top_k, p->iou_thr, ws);
+    k_class_fast_nms<<<dim3(C1, B), kThreads, 0, stream>>>(cls, A, C1, p->top_k, p->iou_thr, ws);
     YB_CHECK_LAUNCH();
   } else {
     YB_REQUIRE(A <= 49152, YB_ERR_UNSUPPORTED, "yb_detect(traditional): num_anchors=%d > 49152", A);
