@@ -25,6 +25,8 @@ Rank 0 prints ONE JSON line:
   parity               the TIMED B=64 output itself: images 0/31/63 vs the fp32 oracle and bit-wise vs B=1 runs; N > 1: the
                        gathered records vs rank 0 re-running every rank's batch on one GPU, bit-for-bit.
   other_configs        BASELINE configs[1] (res50 bs32), configs[4] (swin_tiny bs32) and the 544 variants, N = 1.
+  training             BASELINE configs[3]: res101 550x550 training step (native engine forward + backward + SGD), bs 2 per GPU, DDP over
+                       NCCL at N > 1; at N = 1 beside the same step on torch autograd / cuDNN.
 `--impl reference` times the reference's CPU implementation of the path (the reference itself when staged, else the port).
 """
 import argparse
@@ -272,6 +274,77 @@ def measure_config(arch, img_size, batch, precision, dev, steps, pk):
             'tensor_frac_of_peak': v * gf * 1e9 / (pk['tf_sustained'] * 1e12) if gf else None}
 
 
+def training_leg(arch, img_size, per_gpu, steps, dev, rank, world):
+    """BASELINE.json configs[3]: res101_coco 550x550 training, bs per GPU = 2 (DDP 8x2 at N = 8), synthetic targets (3 boxes per image,
+    seed 1 + rank), SGD lr 0.002 momentum 0.9 wd 5e-4 (config.py:97-100), `steps` timed steps.  The step is Yolact.forward in train mode
+    (native engine: forward + targets + losses) + loss.backward() (native backward) + optimizer.step(); under torchrun the module is
+    wrapped in DistributedDataParallel (train.py:76) and the gradient all-reduce runs over NCCL.  Beside it, at N = 1: the same step
+    on the reference's own GPU path (torch autograd over cuDNN: oracle/train_torch.py, TF32 default, cudnn.benchmark)."""
+    import torch
+    import torch.distributed as dist
+    from oracle import synth, forward_torch as ft, train_torch as tt
+    from yolact_minimal_b200.config import make_config
+    from yolact_minimal_b200.modules.yolact import Yolact
+
+    def make():
+        cfg = make_config(arch + '_coco', img_size, mode='train', train_bs=per_gpu)
+        net = Yolact(cfg)
+        net.load_state_dict(ft.synth_state_dict(arch, seed=0, train=True), strict=True)
+        return net.to(dev).train()
+    img = torch.from_numpy(synth.image_batch(100 + rank, per_gpu, img_size)).to(dev)
+    tg, mk = synth.train_targets(1 + rank, per_gpu, img_size)
+    tgt = [torch.from_numpy(t).to(dev) for t in tg]
+    mks = [torch.from_numpy(m).to(dev) for m in mk]
+    out = {'workload': f'{arch}_coco {img_size}x{img_size} training, bs={per_gpu}/GPU x {world} GPU(s), synthetic targets, SGD', 'steps': steps}
+
+    def run(net, fwd, n):
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=True) if world > 1 else net
+        opt = torch.optim.SGD(model.parameters(), lr=0.002, momentum=0.9, weight_decay=5e-4)
+        first = None
+
+        def step(_):
+            nonlocal first
+            losses = fwd(model)
+            if first is None:
+                first = [float(l.detach()) for l in losses]
+            opt.zero_grad(set_to_none=True)
+            sum(losses).backward()
+            opt.step()
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = cuda_time(step, n)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), first
+    try:
+        net = make()
+        ms, first = run(net, lambda m: m(img, tgt, mks), steps)
+        out.update(value=world * per_gpu / (ms / 1e3), unit='img/s', ms_per_step=ms, first_step_losses=first, dtype='bf16 tensor-core operands, f32 accumulation / statistics / master weights',
+                   launches_per_step=next(iter(net._train_engines.values())).launches_per_step())
+        del net
+        torch.cuda.empty_cache()
+        if world == 1:
+            prev = torch.backends.cudnn.benchmark
+            torch.backends.cudnn.benchmark = True
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            ref = make()
+            ems, efirst = run(ref, lambda m: tt.training_step_forward(m, img, tgt, mks), max(5, steps // 5))
+            torch.backends.cudnn.benchmark = prev
+            out['gpu_eager_baseline'] = {'impl': 'torch autograd over cuDNN / ATen (oracle/train_torch.py: the reference training branch restated), TF32, cudnn.benchmark',
+                                         'img_per_s': per_gpu / (ems / 1e3), 'ms_per_step': ems, 'first_step_losses': efirst,
+                                         'ours_over_eager': (per_gpu / (ms / 1e3)) / (per_gpu / (ems / 1e3))}
+            del ref
+            torch.cuda.empty_cache()
+    except Exception as e:
+        out['error'] = repr(e)[:400]
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -465,6 +538,12 @@ def run_ours(args):
                'd2h_bytes_per_step': world * b * (4 + D * (4 + 4 + 4 + 16 + 128)),
                'api': 'pinned host tensor -> Yolact.forward -> detect_batched -> dist.gather_detections (NCCL) -> D2H of the gathered records'}
 
+    training = None
+    if world > 1 and not os.environ.get('YB_BENCH_QUICK') and (ARCH, IMG) == ('res101', 550):
+        del imgs
+        torch.cuda.empty_cache()
+        training = training_leg(ARCH, IMG, 2, 50, dev, rank, world)           # every rank takes part (DDP all-reduce)
+        imgs = [h.to(dev) for h in host]
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()
@@ -529,6 +608,8 @@ def run_ours(args):
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity': parity}
     if other_scaling:
         line[other_scaling['scaling'] + '_scaling'] = other_scaling
+    if training:
+        line['training'] = training
 
     if world == 1 and not os.environ.get('YB_BENCH_QUICK'):
         # the reference's own GPU path on this box, then the other BASELINE configurations, then the CPU baseline
@@ -543,6 +624,7 @@ def run_ours(args):
                 except Exception as e:
                     oc.append({'workload': f'{a_}_coco {s_}x{s_} bs={b_}', 'error': repr(e)[:200]})
             line['other_configs'] = oc
+            line['training'] = training_leg(ARCH, IMG, 2, 50, dev, 0, 1)
         cores = host_cores()
         cpu_v, cpu_s, cpu_nms_us, kind = cpu_reference_sample(ARCH, IMG, 4, 6, cores)
         line['cpu_baseline'] = {'value': cpu_v, 'unit': 'img/s', 'cores': cores, 'kind': kind,

@@ -13,17 +13,28 @@ import torch.nn.functional as F
 # ----------------------------------------------------------------------------------------------------
 # forward (training mode): raw class logits, box regressions, tanh coefficients, prototypes, seg logits
 # ----------------------------------------------------------------------------------------------------
-def _bottleneck(blk, x):
-    out = F.relu(blk.bn1(blk.conv1(x)))
-    out = F.relu(blk.bn2(blk.conv2(out)))
-    out = blk.bn3(blk.conv3(out))
-    res = x if blk.downsample is None else blk.downsample[1](blk.downsample[0](x))
-    return F.relu(out + res)
+def _conv(m, x, q):
+    """A conv as the native engine computes it when q rounds to its operand type: rounded weights, (already rounded) input."""
+    return F.conv2d(x, q(m.weight), m.bias, m.stride, m.padding)
 
 
-def forward_train(net, img, taps=None):
+def _bottleneck(blk, x, q):
+    out = q(F.relu(blk.bn1(q(_conv(blk.conv1, x, q)))))
+    out = q(F.relu(blk.bn2(q(_conv(blk.conv2, out, q)))))
+    out = blk.bn3(q(_conv(blk.conv3, out, q)))
+    res = x if blk.downsample is None else q(blk.downsample[1](q(_conv(blk.downsample[0], x, q))))
+    return q(F.relu(out + res))
+
+
+def forward_train(net, img, taps=None, act=None):
     """taps: optional dict that receives named intermediate activations (the native engine's tensor names), each with
-    retain_grad() so that their gradients can be compared after backward."""
+    retain_grad() so that their gradients can be compared after backward.
+    act: None = plain fp32 (the reference's arithmetic).  A 16-bit dtype = EMULATE the native engine's rounding points in the forward
+    pass (weights and every stored activation rounded to that type, fp32 accumulation, statistics and network outputs; the cast is
+    differentiable, so autograd still yields fp32 gradients): with identical ReLU masks the engine's gradients can be checked to
+    ~1e-2 instead of the ~sqrt(fraction of flipped masks) that separates any 16-bit forward from an fp32 one."""
+    q = (lambda t: t) if act is None else (lambda t: t.to(act).float())
+
     def tap(name, t):
         if taps is not None:
             if t.requires_grad:
@@ -33,40 +44,45 @@ def forward_train(net, img, taps=None):
     bb = net.backbone
     if not hasattr(bb, 'conv1'):
         raise NotImplementedError('training forward is implemented for the ResNet backbones only')
-    x = tap('pool', F.max_pool2d(tap('stem.z', F.relu(bb.bn1(tap('stem.y', bb.conv1(img))))), kernel_size=3, stride=2, padding=1))
+    x = tap('pool', F.max_pool2d(tap('stem.z', q(F.relu(bb.bn1(tap('stem.y', q(_conv(bb.conv1, q(img), q))))))), kernel_size=3, stride=2, padding=1))
     feats = []
     for stage in bb.layers:
         for i, blk in enumerate(stage):
             if i > 0 and blk.downsample is not None:            # container quirk: only block 0 owns the shortcut
                 raise RuntimeError('unexpected downsample')
-            x = _bottleneck(blk, x)
+            x = _bottleneck(blk, x, q)
         feats.append(tap('c%d' % (len(feats) + 2), x))
     c3, c4, c5 = feats[1:]
     fpn = net.fpn
     up = lambda t, like: F.interpolate(t, size=like.shape[2:], mode='bilinear', align_corners=False)
-    p5_1 = fpn.lat_layers[2](c5)
-    l4 = fpn.lat_layers[1](c4)
-    p4_1 = l4 + up(p5_1, l4)
-    l3 = fpn.lat_layers[0](c3)
-    p3_1 = l3 + up(p4_1, l3)
+    p5_1 = q(_conv(fpn.lat_layers[2], c5, q))
+    l4 = q(_conv(fpn.lat_layers[1], c4, q))
+    p4_1 = q(l4 + up(p5_1, l4))
+    l3 = q(_conv(fpn.lat_layers[0], c3, q))
+    p3_1 = q(l3 + up(p4_1, l3))
     tap('p5_1', p5_1); tap('p4_1', p4_1); tap('p3_1', p3_1)
-    p5, p4, p3 = tap('p5', fpn.pred_layers[2](p5_1)), tap('p4', fpn.pred_layers[1](p4_1)), tap('p3', fpn.pred_layers[0](p3_1))
-    p6 = tap('p6', fpn.downsample_layers[0](p5))
-    p7 = tap('p7', fpn.downsample_layers[1](p6))
+    cr = lambda seq, t: q(F.relu(_conv(seq[0], t, q)))          # conv + ReLU blocks (nn.Sequential(conv, ReLU))
+    p5, p4, p3 = tap('p5', cr(fpn.pred_layers[2], p5_1)), tap('p4', cr(fpn.pred_layers[1], p4_1)), tap('p3', cr(fpn.pred_layers[0], p3_1))
+    p6 = tap('p6', cr(fpn.downsample_layers[0], p5))
+    p7 = tap('p7', cr(fpn.downsample_layers[1], p6))
     levels = (p3, p4, p5, p6, p7)
 
     pn = net.proto_net
-    proto = pn.proto2(tap('proto.up', F.interpolate(tap('proto1.4', pn.proto1(p3)), scale_factor=2, mode='bilinear', align_corners=True)))
-    proto = proto.permute(0, 2, 3, 1).contiguous()
+    t = p3
+    for i in (0, 2, 4):
+        t = q(F.relu(_conv(pn.proto1[i], t, q)))
+    t = tap('proto.up', q(F.interpolate(tap('proto1.4', t), scale_factor=2, mode='bilinear', align_corners=True)))
+    t = q(F.relu(_conv(pn.proto2[0], t, q)))
+    proto = F.relu(_conv(pn.proto2[2], t, q)).permute(0, 2, 3, 1).contiguous()
 
     pl, B = net.prediction_layers, img.shape[0]
     cls, box, coef = [], [], []
     for lv in levels:
-        f = pl.upfeature(lv)
-        cls.append(pl.conf_layer(f).permute(0, 2, 3, 1).reshape(B, -1, pl.num_classes))
-        box.append(pl.bbox_layer(f).permute(0, 2, 3, 1).reshape(B, -1, 4))
-        coef.append(pl.coef_layer(f).permute(0, 2, 3, 1).reshape(B, -1, pl.coef_dim))
-    seg = net.semantic_seg_conv(p3)
+        f = q(F.relu(_conv(pl.upfeature[0], lv, q)))
+        cls.append(_conv(pl.conf_layer, f, q).permute(0, 2, 3, 1).reshape(B, -1, pl.num_classes))
+        box.append(_conv(pl.bbox_layer, f, q).permute(0, 2, 3, 1).reshape(B, -1, 4))
+        coef.append(torch.tanh(_conv(pl.coef_layer[0], f, q)).permute(0, 2, 3, 1).reshape(B, -1, pl.coef_dim))
+    seg = _conv(net.semantic_seg_conv, p3, q)
     return torch.cat(cls, 1), torch.cat(box, 1), torch.cat(coef, 1), proto, seg
 
 
@@ -208,7 +224,7 @@ def compute_loss(net, class_p, box_p, coef_p, proto_p, seg_p, box_classes, masks
             mask_loss(cfg, pos, best_gt, coef_p, proto_p, masks_gt, matched), semantic_loss(cfg, seg_p, masks_gt, class_gt))
 
 
-def training_step_forward(net, img, box_classes, masks_gt, taps=None):
-    """Yolact.forward in training mode: the reference's 4-tuple of losses."""
-    outs = forward_train(net, img, taps)
+def training_step_forward(net, img, box_classes, masks_gt, taps=None, act=None):
+    """Yolact.forward in training mode: the reference's 4-tuple of losses (act: see forward_train)."""
+    outs = forward_train(net, img, taps, act)
     return compute_loss(net, *outs, box_classes, masks_gt)

@@ -96,8 +96,9 @@ def cos(a, b):
 TAPS = ('stem.y', 'stem.z', 'pool', 'c2', 'c3', 'c4', 'c5', 'p5_1', 'p4_1', 'p3_1', 'p3', 'p4', 'p5', 'p6', 'p7', 'proto1.4', 'proto.up')
 
 
-def engine_vs_checker(arch, S, B, dev, precision='bf16', img_seed=11, tgt_seed=5):
-    """One native training step and one checker step (fp32 torch autograd on the GPU, TF32 off) from identical parameters and inputs.
+def engine_vs_checker(arch, S, B, dev, precision='bf16', img_seed=11, tgt_seed=5, emulate=False):
+    """One native training step and one checker step (fp32 torch autograd on the GPU, TF32 off; emulate=True: with the engine's 16-bit
+    rounding points in the forward pass, so that ReLU masks agree) from identical parameters and inputs.
     Returns dict(losses, ref_losses, act={tap: rel err}, gact={tap: rel err of the gradient}, grads={param: (rel err, cosine, ref norm)},
     bn={buffer: max abs err}, launches)."""
     torch.backends.cudnn.allow_tf32 = False
@@ -108,7 +109,8 @@ def engine_vs_checker(arch, S, B, dev, precision='bf16', img_seed=11, tgt_seed=5
     mks = [torch.from_numpy(m).to(dev) for m in mk]
     ref = make_train_net(arch, S, B, dev)
     taps = {}
-    ref_losses = tt.training_step_forward(ref, img, tgt, mks, taps)
+    act = None if not emulate else (torch.bfloat16 if precision == 'bf16' else torch.float16)
+    ref_losses = tt.training_step_forward(ref, img, tgt, mks, taps, act)
     sum(ref_losses).backward()
     net = make_train_net(arch, S, B, dev)
     net.cfg.train_precision = precision

@@ -26,9 +26,9 @@ def stage():
     for k in ('d_cls', 'd_box', 'd_coef', 'd_proto', 'd_seg'):
         print(k, 'rel err', tc.rel(r[k], ref_g[k]), 'cos', tc.cos(r[k], ref_g[k]), 'max abs', float(np.abs(r[k] - ref_g[k]).max()), 'ref norm', float(np.linalg.norm(ref_g[k])))
 
-def engine(arch, S, B, precision):
-    o = tc.engine_vs_checker(arch, S, B, dev, precision)
-    print(f'--- engine {arch}@{S} B={B} {precision}: launches/step {o["launches"]}')
+def engine(arch, S, B, precision, emulate=False):
+    o = tc.engine_vs_checker(arch, S, B, dev, precision, emulate=emulate)
+    print(f'--- engine {arch}@{S} B={B} {precision} emulate={emulate}: launches/step {o["launches"]}')
     print('losses', o['losses'], 'checker', o['ref_losses'])
     print('activations (rel err):', {k: (round(v, 5) if isinstance(v, float) else v) for k, v in o['act'].items()})
     print('activation gradients (rel err):', {k: round(v, 5) for k, v in o['gact'].items()})
@@ -41,7 +41,7 @@ def engine(arch, S, B, precision):
     bn = sorted(o['bn'].items(), key=lambda kv: -kv[1])[:5]
     print('BN buffers worst abs err', bn)
 
-for fn, args in ((stage, ()), (engine, ('res50', 128, 2, 'bf16')), (engine, ('res50', 128, 2, 'fp16')), (engine, ('res101', 96, 2, 'bf16'))):
+for fn, args in ((engine, ('res50', 128, 2, 'bf16', True)), (engine, ('res50', 128, 2, 'fp16', True)), (engine, ('res101', 96, 2, 'bf16', True)), (engine, ('res50', 256, 2, 'bf16', True))):
     try:
         fn(*args)
     except Exception:
