@@ -18,12 +18,13 @@ def _conv(m, x, q):
     return F.conv2d(x, q(m.weight), m.bias, m.stride, m.padding)
 
 
-def _bottleneck(blk, x, q):
-    out = q(F.relu(blk.bn1(q(_conv(blk.conv1, x, q)))))
-    out = q(F.relu(blk.bn2(q(_conv(blk.conv2, out, q)))))
-    out = blk.bn3(q(_conv(blk.conv3, out, q)))
-    res = x if blk.downsample is None else q(blk.downsample[1](q(_conv(blk.downsample[0], x, q))))
-    return q(F.relu(out + res))
+def _bottleneck(blk, x, q, tap=None, name=''):
+    tap = tap or (lambda n, t: t)
+    out = tap(name + '.bn1.z', q(F.relu(blk.bn1(tap(name + '.conv1.y', q(_conv(blk.conv1, x, q)))))))
+    out = tap(name + '.bn2.z', q(F.relu(blk.bn2(tap(name + '.conv2.y', q(_conv(blk.conv2, out, q)))))))
+    out = blk.bn3(tap(name + '.conv3.y', q(_conv(blk.conv3, out, q))))
+    res = x if blk.downsample is None else tap(name + '.downsample.z', q(blk.downsample[1](tap(name + '.downsample.y', q(_conv(blk.downsample[0], x, q))))))
+    return tap(name + '.out', q(F.relu(out + res)))
 
 
 def forward_train(net, img, taps=None, act=None):
@@ -46,11 +47,11 @@ def forward_train(net, img, taps=None, act=None):
         raise NotImplementedError('training forward is implemented for the ResNet backbones only')
     x = tap('pool', F.max_pool2d(tap('stem.z', q(F.relu(bb.bn1(tap('stem.y', q(_conv(bb.conv1, q(img), q))))))), kernel_size=3, stride=2, padding=1))
     feats = []
-    for stage in bb.layers:
+    for si, stage in enumerate(bb.layers):
         for i, blk in enumerate(stage):
             if i > 0 and blk.downsample is not None:            # container quirk: only block 0 owns the shortcut
                 raise RuntimeError('unexpected downsample')
-            x = _bottleneck(blk, x, q)
+            x = _bottleneck(blk, x, q, tap if (si == 0 or i == 0) else None, f'backbone.layers.{si}.{i}')
         feats.append(tap('c%d' % (len(feats) + 2), x))
     c3, c4, c5 = feats[1:]
     fpn = net.fpn

@@ -28,7 +28,7 @@ def _run(cuda, cls, box, coef, anchors, cfg):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
     r = detect_batched(t(cls), t(box), t(coef), t(anchors), cfg)
     torch.cuda.synchronize()
-    return {k: v.cpu().numpy() for k, v in r.items()}
+    return {k: v.cpu().numpy() for k, v in r.items() if not k.startswith('_')}
 
 
 def _check_image(r, b, o, coef):

@@ -120,7 +120,7 @@ def engine_vs_checker(arch, S, B, dev, precision='bf16', img_seed=11, tgt_seed=5
     eng = next(iter(net._train_engines.values()))
     out = dict(losses=[float(l) for l in losses], ref_losses=[float(l) for l in ref_losses], act={}, gact={}, grads={}, bn={},
                launches=eng.launches_per_step())
-    for name in TAPS:
+    for name in list(TAPS) + [n for n in taps if n.startswith('backbone.')]:
         if name not in taps:
             continue
         try:

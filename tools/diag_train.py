@@ -41,7 +41,7 @@ def engine(arch, S, B, precision, emulate=False):
     bn = sorted(o['bn'].items(), key=lambda kv: -kv[1])[:5]
     print('BN buffers worst abs err', bn)
 
-for fn, args in ((engine, ('res50', 128, 2, 'bf16', True)), (engine, ('res50', 128, 2, 'fp16', True)), (engine, ('res101', 96, 2, 'bf16', True)), (engine, ('res50', 256, 2, 'bf16', True))):
+for fn, args in ((engine, ('res50', 128, 2, 'bf16', True)),):
     try:
         fn(*args)
     except Exception:

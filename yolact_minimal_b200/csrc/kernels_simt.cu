@@ -388,44 +388,56 @@ int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hi
 // [B, A, C] / [B, A, 4] / [B, A, K] layout (modules/yolact.py:26-31,:155-163).
 // head row layout: [conf: R*C | box: R*4 | coef: R*K | pad]
 // ------------------------------------------------------------------------------------------------
+// Each warp handles kHeadItems consecutive (pixel, anchor) items and issues ALL their loads before the first reduction: with one
+// item per warp the kernel was latency-bound (a handful of loads in flight per warp, ~2 us per warp lifetime, 0.5 ms per forward).
+constexpr int kHeadItems = 4;
+
 __global__ void __launch_bounds__(256) k_head_finalize(const float* __restrict__ head, int ld, int HW, int R, int NC, int K,
                                                        int anchor_offset, int A_total, float* __restrict__ cls,
                                                        float* __restrict__ box, float* __restrict__ coef) {
   const int lane = threadIdx.x & 31;
-  const int wi = blockIdx.x * 8 + (threadIdx.x >> 5);              // (pixel, anchor) within the image
-  if (wi >= HW * R) return;
+  const int wi0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kHeadItems;  // first (pixel, anchor) item of this warp
+  const int n_items = HW * R;
+  if (wi0 >= n_items) return;
   const int b = blockIdx.y;
-  const int pix = wi / R, a = wi - pix * R;
-  const float* row = head + ((size_t)b * HW + pix) * ld;
-  const size_t arow = (size_t)b * A_total + anchor_offset + (size_t)pix * R + a;
-  const float* lg = row + a * NC;
-  float mx = -INFINITY;
-  for (int c = lane; c < NC; c += 32) mx = fmaxf(mx, lg[c]);
+  float lg[kHeadItems][4], bx[kHeadItems], cf[kHeadItems][2];          // NC <= 128, K <= 64
+  size_t arow[kHeadItems];
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-  float ex[4] = {0.f, 0.f, 0.f, 0.f};                              // NC <= 128
-  float sum = 0.f;
+  for (int it = 0; it < kHeadItems; ++it) {
+    const int wi = min(wi0 + it, n_items - 1);                         // clamp: the tail warp recomputes its last item
+    const int pix = wi / R, a = wi - pix * R;
+    const float* row = head + ((size_t)b * HW + pix) * ld;
+    arow[it] = (size_t)b * A_total + anchor_offset + (size_t)pix * R + a;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = lane + 32 * i;
-    if (c < NC) { ex[i] = __expf(lg[c] - mx); sum += ex[i]; }
+    for (int i = 0; i < 4; ++i) { const int c = lane + 32 * i; lg[it][i] = c < NC ? __ldg(row + a * NC + c) : -INFINITY; }
+    bx[it] = lane < 4 ? __ldg(row + R * NC + a * 4 + lane) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const int k = lane + 32 * i; cf[it][i] = k < K ? __ldg(row + R * NC + R * 4 + a * K + k) : 0.f; }
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  const float inv = 1.f / sum;
+  for (int it = 0; it < kHeadItems; ++it) {
+    if (wi0 + it >= n_items) break;
+    float mx = fmaxf(fmaxf(lg[it][0], lg[it][1]), fmaxf(lg[it][2], lg[it][3]));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = lane + 32 * i;
-    if (c < NC) cls[arow * NC + c] = ex[i] * inv;
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float ex[4], sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ex[i] = (lane + 32 * i) < NC ? __expf(lg[it][i] - mx) : 0.f; sum += ex[i]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int c = lane + 32 * i; if (c < NC) cls[arow[it] * NC + c] = ex[i] * inv; }
+    if (lane < 4) box[arow[it] * 4 + lane] = bx[it];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const int k = lane + 32 * i; if (k < K) coef[arow[it] * K + k] = tanhf(cf[it][i]); }
   }
-  if (lane < 4) box[arow * 4 + lane] = row[R * NC + a * 4 + lane];
-  for (int k = lane; k < K; k += 32) coef[arow * K + k] = tanhf(row[R * NC + R * 4 + a * K + k]);
 }
 
 int launch_head_finalize(const float* head, int ld, int B, int HW, int R, int NC, int K, int anchor_offset, int A_total,
                          float* cls, float* box, float* coef, cudaStream_t s) {
-  YB_REQUIRE(NC <= 128, YB_ERR_UNSUPPORTED, "head_finalize: num_classes=%d > 128", NC);
-  dim3 grid(ceil_div(HW * R, 8), B);
+  YB_REQUIRE(NC <= 128 && K <= 64, YB_ERR_UNSUPPORTED, "head_finalize: num_classes=%d > 128 or coef_dim=%d > 64", NC, K);
+  dim3 grid(ceil_div(HW * R, 8 * kHeadItems), B);
   k_head_finalize<<<grid, 256, 0, s>>>(head, ld, HW, R, NC, K, anchor_offset, A_total, cls, box, coef);
   YB_CHECK_LAUNCH();
   return YB_OK;
