@@ -27,7 +27,7 @@ def _bottleneck(blk, x, q, tap=None, name=''):
     return tap(name + '.out', q(F.relu(out + res)))
 
 
-def forward_train(net, img, taps=None, act=None):
+def forward_train(net, img, taps=None, act=None, subst=None):
     """taps: optional dict that receives named intermediate activations (the native engine's tensor names), each with
     retain_grad() so that their gradients can be compared after backward.
     act: None = plain fp32 (the reference's arithmetic).  A 16-bit dtype = EMULATE the native engine's rounding points in the forward
@@ -37,6 +37,14 @@ def forward_train(net, img, taps=None, act=None):
     q = (lambda t: t) if act is None else (lambda t: t.to(act).float())
 
     def tap(name, t):
+        if subst is not None:
+            # evaluate the rest of the network (and hence the whole backward pass) AT THE ENGINE'S OWN ACTIVATIONS: the value is
+            # replaced by what the engine stored for this tensor, the gradient still flows into the checker's graph.  With identical
+            # values every ReLU mask and batch statistic agrees, so gradients can be compared to ~1e-2 instead of the
+            # sqrt(fraction of flipped masks) that separates two independently rounded 16-bit forwards.
+            v = subst(name)
+            if v is not None:
+                t = v.to(t.dtype) + (t - t.detach())
         if taps is not None:
             if t.requires_grad:
                 t.retain_grad()
@@ -51,7 +59,7 @@ def forward_train(net, img, taps=None, act=None):
         for i, blk in enumerate(stage):
             if i > 0 and blk.downsample is not None:            # container quirk: only block 0 owns the shortcut
                 raise RuntimeError('unexpected downsample')
-            x = _bottleneck(blk, x, q, tap if (si == 0 or i == 0) else None, f'backbone.layers.{si}.{i}')
+            x = _bottleneck(blk, x, q, tap, f'backbone.layers.{si}.{i}')
         feats.append(tap('c%d' % (len(feats) + 2), x))
     c3, c4, c5 = feats[1:]
     fpn = net.fpn
@@ -71,15 +79,15 @@ def forward_train(net, img, taps=None, act=None):
     pn = net.proto_net
     t = p3
     for i in (0, 2, 4):
-        t = q(F.relu(_conv(pn.proto1[i], t, q)))
-    t = tap('proto.up', q(F.interpolate(tap('proto1.4', t), scale_factor=2, mode='bilinear', align_corners=True)))
-    t = q(F.relu(_conv(pn.proto2[0], t, q)))
+        t = tap(f'proto1.{i}', q(F.relu(_conv(pn.proto1[i], t, q))))
+    t = tap('proto.up', q(F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=True)))
+    t = tap('proto2.0', q(F.relu(_conv(pn.proto2[0], t, q))))
     proto = F.relu(_conv(pn.proto2[2], t, q)).permute(0, 2, 3, 1).contiguous()
 
     pl, B = net.prediction_layers, img.shape[0]
     cls, box, coef = [], [], []
-    for lv in levels:
-        f = q(F.relu(_conv(pl.upfeature[0], lv, q)))
+    for li, lv in enumerate(levels):
+        f = tap(f'head.f{li}', q(F.relu(_conv(pl.upfeature[0], lv, q))))
         cls.append(_conv(pl.conf_layer, f, q).permute(0, 2, 3, 1).reshape(B, -1, pl.num_classes))
         box.append(_conv(pl.bbox_layer, f, q).permute(0, 2, 3, 1).reshape(B, -1, 4))
         coef.append(torch.tanh(_conv(pl.coef_layer[0], f, q)).permute(0, 2, 3, 1).reshape(B, -1, pl.coef_dim))
@@ -225,7 +233,7 @@ def compute_loss(net, class_p, box_p, coef_p, proto_p, seg_p, box_classes, masks
             mask_loss(cfg, pos, best_gt, coef_p, proto_p, masks_gt, matched), semantic_loss(cfg, seg_p, masks_gt, class_gt))
 
 
-def training_step_forward(net, img, box_classes, masks_gt, taps=None, act=None):
-    """Yolact.forward in training mode: the reference's 4-tuple of losses (act: see forward_train)."""
-    outs = forward_train(net, img, taps, act)
+def training_step_forward(net, img, box_classes, masks_gt, taps=None, act=None, subst=None):
+    """Yolact.forward in training mode: the reference's 4-tuple of losses (act / subst: see forward_train)."""
+    outs = forward_train(net, img, taps, act, subst)
     return compute_loss(net, *outs, box_classes, masks_gt)

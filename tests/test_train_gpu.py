@@ -69,7 +69,7 @@ def test_native_losses_random_subset_when_many_positives(cuda):
 
 @pytest.mark.parametrize('arch,S,B', [('res50', 128, 2), ('res101', 96, 2)])
 def test_training_engine_vs_checker(cuda, arch, S, B):
-    o = tc.engine_vs_checker(arch, S, B, cuda, 'bf16')
+    o = tc.engine_vs_checker(arch, S, B, cuda, 'bf16')          # vs the reference's fp32 arithmetic
     g = load_golden('train.npz')
     gold = g[f'{arch}_S{S}_B{B}/losses']
     print('losses', o['losses'], 'checker', o['ref_losses'], 'reference golden', gold.tolist(), 'launches/step', o['launches'])

@@ -96,9 +96,12 @@ def cos(a, b):
 TAPS = ('stem.y', 'stem.z', 'pool', 'c2', 'c3', 'c4', 'c5', 'p5_1', 'p4_1', 'p3_1', 'p3', 'p4', 'p5', 'p6', 'p7', 'proto1.4', 'proto.up')
 
 
-def engine_vs_checker(arch, S, B, dev, precision='bf16', img_seed=11, tgt_seed=5, emulate=False):
-    """One native training step and one checker step (fp32 torch autograd on the GPU, TF32 off; emulate=True: with the engine's 16-bit
-    rounding points in the forward pass, so that ReLU masks agree) from identical parameters and inputs.
+def engine_vs_checker(arch, S, B, dev, precision='bf16', img_seed=11, tgt_seed=5, mode='fp32'):
+    """One native training step and one checker step (torch autograd on the GPU, TF32 off) from identical parameters and inputs.
+    mode 'fp32'      the reference's arithmetic: how far a 16-bit training step is from fp32 (losses, gradient direction)
+         'emulate'   the checker's forward rounds where the engine rounds (oracle/train_torch.forward_train act=)
+         'subst'     the checker is evaluated AT the engine's stored activations (forward_train subst=): identical ReLU masks and
+                     batch statistics, so the comparison isolates the engine's BACKWARD arithmetic (dgrad / wgrad / BN / pooling / ...)
     Returns dict(losses, ref_losses, act={tap: rel err}, gact={tap: rel err of the gradient}, grads={param: (rel err, cosine, ref norm)},
     bn={buffer: max abs err}, launches)."""
     torch.backends.cudnn.allow_tf32 = False
@@ -107,25 +110,33 @@ def engine_vs_checker(arch, S, B, dev, precision='bf16', img_seed=11, tgt_seed=5
     tg, mk = synth.train_targets(tgt_seed, B, S)
     tgt = [torch.from_numpy(t).to(dev) for t in tg]
     mks = [torch.from_numpy(m).to(dev) for m in mk]
-    ref = make_train_net(arch, S, B, dev)
-    taps = {}
-    act = None if not emulate else (torch.bfloat16 if precision == 'bf16' else torch.float16)
-    ref_losses = tt.training_step_forward(ref, img, tgt, mks, taps, act)
-    sum(ref_losses).backward()
     net = make_train_net(arch, S, B, dev)
     net.cfg.train_precision = precision
     losses = net(img, tgt, mks)
     sum(losses).backward()
     torch.cuda.synchronize()
     eng = next(iter(net._train_engines.values()))
-    out = dict(losses=[float(l) for l in losses], ref_losses=[float(l) for l in ref_losses], act={}, gact={}, grads={}, bn={},
-               launches=eng.launches_per_step())
-    for name in list(TAPS) + [n for n in taps if n.startswith('backbone.')]:
-        if name not in taps:
-            continue
+    ref = make_train_net(arch, S, B, dev)
+    taps = {}
+    act = (torch.bfloat16 if precision == 'bf16' else torch.float16) if mode in ('emulate', 'subst') else None
+    cache = {}
+
+    def subst(name):
+        if name not in cache:
+            try:
+                cache[name] = eng.read(name)
+            except Exception:
+                cache[name] = None
+        return cache[name]
+    ref_losses = tt.training_step_forward(ref, img, tgt, mks, taps, act, subst if mode == 'subst' else None)
+    sum(ref_losses).backward()
+    out = dict(losses=[float(l.detach()) for l in losses], ref_losses=[float(l.detach()) for l in ref_losses], act={}, gact={}, grads={}, bn={},
+               launches=eng.launches_per_step(), substituted=sum(v is not None for v in cache.values()))
+    relu_out = lambda n: n in ('p3', 'p4', 'p5', 'p6', 'p7', 'proto2.0') or n.startswith(('proto1.', 'head.f'))     # the engine masks these gradients in place
+    for name in taps:
         try:
             out['act'][name] = rel(eng.read(name).cpu().numpy(), taps[name].detach().cpu().numpy())
-            if taps[name].grad is not None:
+            if taps[name].grad is not None and not relu_out(name):
                 out['gact'][name] = rel(eng.read(name, grad=True).cpu().numpy(), taps[name].grad.cpu().numpy())
         except Exception as e:                                        # a tap without a gradient buffer etc.
             out['act'].setdefault(name, repr(e)[:80])

@@ -26,12 +26,13 @@ def stage():
     for k in ('d_cls', 'd_box', 'd_coef', 'd_proto', 'd_seg'):
         print(k, 'rel err', tc.rel(r[k], ref_g[k]), 'cos', tc.cos(r[k], ref_g[k]), 'max abs', float(np.abs(r[k] - ref_g[k]).max()), 'ref norm', float(np.linalg.norm(ref_g[k])))
 
-def engine(arch, S, B, precision, emulate=False):
-    o = tc.engine_vs_checker(arch, S, B, dev, precision, emulate=emulate)
-    print(f'--- engine {arch}@{S} B={B} {precision} emulate={emulate}: launches/step {o["launches"]}')
+def engine(arch, S, B, precision, mode='fp32'):
+    o = tc.engine_vs_checker(arch, S, B, dev, precision, mode=mode)
+    print(f'--- engine {arch}@{S} B={B} {precision} mode={mode}: launches/step {o["launches"]} substituted {o["substituted"]}')
     print('losses', o['losses'], 'checker', o['ref_losses'])
-    print('activations (rel err):', {k: (round(v, 5) if isinstance(v, float) else v) for k, v in o['act'].items()})
-    print('activation gradients (rel err):', {k: round(v, 5) for k, v in o['gact'].items()})
+    big = lambda d: {k: (round(v, 5) if isinstance(v, float) else v) for k, v in sorted(d.items(), key=lambda kv: -(kv[1] if isinstance(kv[1], float) else 9))[:24]}
+    print('activations (rel err), worst 24:', big(o['act']))
+    print('activation gradients (rel err), worst 24:', big(o['gact']))
     worst = sorted(o['grads'].items(), key=lambda kv: -(kv[1][0] if kv[1][0] == kv[1][0] else 1e9))
     print('parameter gradients, worst 40 by rel err (rel, cos, ref norm):')
     for n, v in worst[:40]:
@@ -41,7 +42,7 @@ def engine(arch, S, B, precision, emulate=False):
     bn = sorted(o['bn'].items(), key=lambda kv: -kv[1])[:5]
     print('BN buffers worst abs err', bn)
 
-for fn, args in ((engine, ('res50', 128, 2, 'bf16', True)),):
+for fn, args in ((engine, ('res50', 128, 2, 'bf16', 'subst')), (engine, ('res50', 128, 2, 'fp16', 'subst')), (engine, ('res101', 96, 2, 'bf16', 'subst'))):
     try:
         fn(*args)
     except Exception:

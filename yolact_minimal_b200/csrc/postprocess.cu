@@ -26,9 +26,10 @@ constexpr int kP1Anchors = 128;   // anchors per phase-1 tile
 constexpr int kThreads = 256;
 constexpr int kSortCap = 256;     // top_k, max_det <= 256
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kListCap = 4096;   // entries per (image, class) candidate list == the compact capacity of the per-class kernel
+constexpr int kListCap = 2048;   // entries per (image, class) candidate list == the compact capacity of the per-class kernel
 constexpr int kBins = 116;        // sampled-score histogram: 8 bins per binary exponent over [2^-14, 1), + underflow / overflow
-constexpr int kSamples = 1024, kSampleBlocks = 8;
+constexpr int kSamples = 1024;    // sampled anchors per image (one thread each)
+constexpr int kStage = 16;        // per-class staging slots of a phase-1 tile before one global append per class
 
 struct DetectWs {
   int* cand_count;    // [B]
@@ -139,49 +140,31 @@ __device__ __forceinline__ float bin_lower_edge(int bin) {
   return __uint_as_float(((uint32_t)(e + 127) << 23) | ((uint32_t)m << 20));
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kSamples)
 k_sample_cuts(const float* __restrict__ cls, int A, int C, float score_thr, int top_k, DetectWs ws) {
   extern __shared__ int s_hist[];                         // [C1][kBins]
-  __shared__ int s_cnt, s_last;
-  const int b = blockIdx.y, tid = threadIdx.x, C1 = C - 1;
-  const int per_block = kSamples / kSampleBlocks;         // 128 samples, two threads each
-  for (int i = tid; i < C1 * kBins; i += kThreads) s_hist[i] = 0;
+  __shared__ int s_cnt;
+  const int b = blockIdx.x, tid = threadIdx.x, C1 = C - 1;
+  for (int i = tid; i < C1 * kBins; i += kSamples) s_hist[i] = 0;
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  const int la = tid >> 1, half = tid & 1;
-  const int si = blockIdx.x * per_block + la;             // sample index
-  const long long a = ((long long)si * A) / kSamples;     // strided anchors
+  const long long a = ((long long)tid * A) / kSamples;    // strided anchors, one per thread
   const float* row = cls + ((size_t)b * A + (size_t)a) * C;
   float m = -INFINITY; bool has_nan = false;
-  for (int c = 1 + half; c < C; c += 2) { const float v = __ldg(row + c); has_nan |= (v != v); m = v > m ? v : m; }
-  const float mo = __shfl_xor_sync(kFull, m, 1);
-  const bool no = __shfl_xor_sync(kFull, (int)has_nan, 1) != 0;
-  m = mo > m ? mo : m; has_nan |= no;
-  const bool cand = !has_nan && m > score_thr;
-  if (cand) {
-    if (half == 0) atomicAdd(&s_cnt, 1);
-    for (int c = 1 + half; c < C; c += 2) atomicAdd(&s_hist[(c - 1) * kBins + score_bin(__ldg(row + c))], 1);
+  for (int c = 1; c < C; ++c) { const float v = __ldg(row + c); has_nan |= (v != v); m = v > m ? v : m; }
+  if (!has_nan && m > score_thr) {                        // a candidate (output_utils.py:140-143): histogram its class scores
+    atomicAdd(&s_cnt, 1);
+    for (int c = 1; c < C; ++c) atomicAdd(&s_hist[(c - 1) * kBins + score_bin(__ldg(row + c))], 1);
   }
   __syncthreads();
-  int* gh = ws.hist + (size_t)b * C1 * kBins;
-  for (int i = tid; i < C1 * kBins; i += kThreads) { const int v = s_hist[i]; if (v) atomicAdd(&gh[i], v); }
-  if (tid == 0 && s_cnt) atomicAdd(&ws.samp[b * 2], s_cnt);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(&ws.samp[b * 2 + 1], 1) == (int)gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // the last block of the image turns the histogram into cuts
-  const int cnt = atomicAdd(&ws.samp[b * 2], 0);
-  const double est_n = (double)cnt * A / kSamples;        // estimated number of candidates of the image
-  for (int c = tid; c < C1; c += kThreads) {
+  const double est_n = (double)s_cnt * A / kSamples;      // estimated number of candidates of the image
+  for (int c = tid; c < C1; c += kSamples) {
     uint32_t cut = 0u;
     if (est_n > 0.6 * kListCap) {                         // otherwise every candidate fits the list: take all
       const int want = (int)(3.0 * top_k * kSamples / A) + 8;      // sampled rank of ~3 top_k survivors, + margin
       int acc = 0;
       for (int bin = kBins - 1; bin > 0; --bin) {
-        acc += atomicAdd(&gh[c * kBins + bin], 0);
+        acc += s_hist[c * kBins + bin];
         if (acc >= want) { cut = float_to_ordered(bin_lower_edge(bin)); break; }
       }
     }
@@ -198,6 +181,7 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
                 int A, int C, float score_thr, int no_clip, DetectWs ws) {
   extern __shared__ float tile[];                 // [kP1Anchors * C]
   __shared__ int s_kept[kP1Anchors];
+  __shared__ int s_local[kP1Anchors];              // slot of the anchor inside this tile's kept list, -1 = not a candidate
   __shared__ int s_warp_cnt[kThreads / 32];
   __shared__ int s_warp_off[kThreads / 32];
   __shared__ int s_base, s_total;
@@ -243,9 +227,12 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
   __syncthreads();
   const int total = s_total, base = s_base;
   if (total == 0) return;
+  if (half == 0 && la < kP1Anchors) s_local[la] = -1;
+  __syncwarp();
   if (keep) {
     const int local = s_warp_off[w] + __popc(bal & ((1u << lane) - 1u));
     s_kept[local] = la;
+    s_local[la] = local;
     const int a = a0 + la;
     const size_t slot = (size_t)b * A + base + local;
     ws.cand_anchor[slot] = a;
@@ -263,32 +250,36 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
     }
     return;
   }
-  // per-class candidate lists: warp w takes classes w, w+8, ...; an entry is appended iff its score key reaches the class's cut
-  for (int c = w; c < C1; c += kThreads / 32) {
-    const uint32_t cut = ws.cut[(size_t)b * C1 + c];
-    int cnt = 0;
-    for (int j0 = 0; j0 < total; j0 += 32) {
-      const int j = j0 + lane;
-      const bool take = j < total && float_to_ordered(tile[s_kept[j] * C + c + 1]) >= cut;
-      cnt += __popc(__ballot_sync(kFull, take));
-    }
-    if (cnt == 0) continue;                                            // warp-uniform
-    int lbase = 0;
-    if (lane == 0) lbase = atomicAdd(&ws.list_cnt[(size_t)b * C1 + c], cnt);
-    lbase = __shfl_sync(kFull, lbase, 0);
-    uint2* dst = ws.list + ((size_t)b * C1 + c) * kListCap;
-    for (int j0 = 0; j0 < total; j0 += 32) {
-      const int j = j0 + lane;
-      uint32_t key = 0u;
-      bool take = false;
-      if (j < total) { key = float_to_ordered(tile[s_kept[j] * C + c + 1]); take = key >= cut; }
-      const unsigned bal = __ballot_sync(kFull, take);
-      if (take) {
-        const int pos = lbase + __popc(bal & ((1u << lane) - 1u));
-        if (pos < kListCap) dst[pos] = make_uint2(key, (uint32_t)(base + j));
+  // per-class candidate lists.  The two threads of a kept anchor walk its even / odd classes; a score that reaches the class's cut
+  // (a few per cent of them) is staged in shared memory, and each class is flushed to its global list with ONE atomic per tile.
+  __shared__ int s_ccnt[128];                          // C1 <= 128 on this path
+  __shared__ uint32_t s_cut[128];
+  uint2* s_stage = reinterpret_cast<uint2*>(tile + (size_t)kP1Anchors * C + (((size_t)kP1Anchors * C) & 1));   // [C1][kStage], behind the tile (8-byte aligned)
+  for (int c = tid; c < C1; c += kThreads) { s_ccnt[c] = 0; s_cut[c] = ws.cut[(size_t)b * C1 + c]; }
+  __syncthreads();
+  if (la < na && s_local[la] >= 0) {                   // kept anchor (both threads of the pair)
+    const uint32_t slot = (uint32_t)(base + s_local[la]);
+    const float* row = tile + la * C;
+    for (int c = 1 + half; c < C; c += 2) {
+      const uint32_t key = float_to_ordered(row[c]);
+      if (key >= s_cut[c - 1]) {
+        const int pos = atomicAdd(&s_ccnt[c - 1], 1);
+        if (pos < kStage) s_stage[(c - 1) * kStage + pos] = make_uint2(key, slot);
+        else {                                           // tile-local overflow (cut 0 on a dense tile): append directly
+          const int g = atomicAdd(&ws.list_cnt[(size_t)b * C1 + c - 1], 1);
+          if (g < kListCap) ws.list[((size_t)b * C1 + c - 1) * kListCap + g] = make_uint2(key, slot);
+        }
       }
-      lbase += __popc(bal);
     }
+  }
+  __syncthreads();
+  for (int c = w; c < C1; c += kThreads / 32) {          // one warp per class: flush the staged entries
+    const int cnt = min(s_ccnt[c], kStage);
+    if (cnt == 0) continue;
+    int g = 0;
+    if (lane == 0) g = atomicAdd(&ws.list_cnt[(size_t)b * C1 + c], cnt);
+    g = __shfl_sync(kFull, g, 0);
+    if (lane < cnt && g + lane < kListCap) ws.list[((size_t)b * C1 + c) * kListCap + g + lane] = s_stage[c * kStage + lane];
   }
 }
 
@@ -370,7 +361,7 @@ __device__ void bitonic_sort_256(unsigned long long* key, int* val) {
 //            bitonic sort of the <= 256 winners by (score desc, anchor asc)
 //   stage 3  k x k IoU upper triangle, keep rule, ordered compaction of the survivors
 // --------------------------------------------------------------------------------------------
-constexpr int kCompactCap = 4096;
+constexpr int kCompactCap = kListCap;
 
 __device__ void bitonic_sort_256_desc_u32(uint32_t* key) {
   const int tid = threadIdx.x;
@@ -470,8 +461,17 @@ k_class_fast_nms(const float* __restrict__ cls, int A, int C1, int top_k, float 
     }
   }
   __syncthreads();
-  for (int i = k + tid; i < kSortCap; i += kThreads) { s_sort[i] = ~0ull; s_slot[i] = -1; }
-  bitonic_sort_256(s_sort, s_slot);
+  {  // sort the k winners by (score desc, anchor asc): the 64-bit keys are distinct, so an element's sorted position is the number of
+     // smaller keys -- one pass of broadcast shared-memory reads instead of the 36 barrier steps of a 256-element bitonic network
+    unsigned long long mykey = 0ull; int myslot = -1, rank = 0;
+    if (tid < k) {
+      mykey = s_sort[tid]; myslot = s_slot[tid];
+      for (int j = 0; j < k; ++j) rank += s_sort[j] < mykey ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid < k) { s_sort[rank] = mykey; s_slot[rank] = myslot; }
+    __syncthreads();
+  }
 
   // ---- stage 3: Fast-NMS keep rule ----------------------------------------------------------------
   const float4* cbox = ws.cand_box + (size_t)b * A;
@@ -758,7 +758,7 @@ static int check_params(const yb_detect_params* p, int batch, int A) {
   YB_REQUIRE(p->max_det >= 1 && p->max_det <= kSortCap, YB_ERR_UNSUPPORTED, "yb_detect: max_det=%d outside [1,%d]", p->max_det, kSortCap);
   YB_REQUIRE(p->coef_dim >= 0, YB_ERR_INVALID, "yb_detect: coef_dim=%d", p->coef_dim);
   YB_REQUIRE((double)(p->num_classes - 1) * A < 4294967296.0, YB_ERR_UNSUPPORTED, "yb_detect: (C-1)*A overflows 32 bits");
-  YB_REQUIRE((size_t)kP1Anchors * p->num_classes * 4 <= 200 * 1024, YB_ERR_UNSUPPORTED, "yb_detect: num_classes=%d too large", p->num_classes);
+  YB_REQUIRE(p->num_classes <= 129, YB_ERR_UNSUPPORTED, "yb_detect: num_classes=%d > 129", p->num_classes);
   return YB_OK;
 }
 
@@ -796,14 +796,14 @@ extern "C" int yb_detect(const float* cls, const float* box, const float* coef, 
       YB_CHECK_CUDA(cudaMemsetAsync(ws.cut, 0, (size_t)((char*)ws.list - (char*)ws.cut), stream));
       YB_CHECK_CUDA(cudaMemsetAsync(ws.samp, 0, sizeof(int) * (size_t)B * 2, stream));
       if (A > kListCap) {                                     // small heads: every candidate fits its list, no sampling
-        YB_CHECK_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(int) * (size_t)B * C1 * kBins, stream));
         const size_t hs = (size_t)C1 * kBins * sizeof(int);
         YB_CHECK_CUDA(cudaFuncSetAttribute(k_sample_cuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-        k_sample_cuts<<<dim3(kSampleBlocks, B), kThreads, hs, stream>>>(cls, A, C, p->score_thr, p->top_k, ws);
+        k_sample_cuts<<<B, kSamples, hs, stream>>>(cls, A, C, p->score_thr, p->top_k, ws);
         YB_CHECK_LAUNCH();
       }
-      YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_filter_decode<true><<<grid, kThreads, smem, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
+      const size_t smem2 = smem + 8 + (size_t)C1 * kStage * sizeof(uint2);
+      YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_filter_decode<true><<<grid, kThreads, smem2, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
     }
     YB_CHECK_LAUNCH();
   }
