@@ -169,10 +169,11 @@ def test_fp16_range_relative_error_and_saturation(cuda):
     w = (synth.normal(21, 2, (Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32)
     b = np.zeros(Cout, np.float32)
     q = lambda t: torch.from_numpy(t).to(cuda).half().double()
-    for scale, saturates in ((6.0e3, False), (6.0e4, True)):
+    for scale, wscale, saturates in ((6.0e3, 1.0, False), (1.0e4, 4.0, True)):      # inputs stay inside the fp16 range, outputs may not
         xs = (x * np.float32(scale)).astype(np.float32)
-        y = run_conv(cuda, xs, w, b, None, k, 1, 0, 2, 1).double()
-        ref = F.conv2d(q(xs), q(w), None, padding=1)
+        ws = (w * np.float32(wscale)).astype(np.float32)
+        y = run_conv(cuda, xs, ws, b, None, k, 1, 0, 2, 1).double()
+        ref = F.conv2d(q(xs), q(ws), None, padding=1)
         assert torch.isfinite(y).all()
         if not saturates:
             assert float(ref.abs().max()) > 2.0e4                              # the case really is near the top of the range

@@ -273,13 +273,17 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
     }
   }
   __syncthreads();
-  for (int c = w; c < C1; c += kThreads / 32) {          // one warp per class: flush the staged entries
+  // flush: one global atomic per class with staged entries, ALL issued at once (thread c reserves class c's range; a warp that
+  // reserves and writes class after class pays one global round trip per class, which dominated this kernel), then the copies
+  __shared__ int s_gbase[128];
+  for (int c = tid; c < C1; c += kThreads) {
     const int cnt = min(s_ccnt[c], kStage);
-    if (cnt == 0) continue;
-    int g = 0;
-    if (lane == 0) g = atomicAdd(&ws.list_cnt[(size_t)b * C1 + c], cnt);
-    g = __shfl_sync(kFull, g, 0);
-    if (lane < cnt && g + lane < kListCap) ws.list[((size_t)b * C1 + c) * kListCap + g + lane] = s_stage[c * kStage + lane];
+    s_gbase[c] = cnt ? atomicAdd(&ws.list_cnt[(size_t)b * C1 + c], cnt) : 0;
+  }
+  __syncthreads();
+  for (int e = tid; e < C1 * kStage; e += kThreads) {
+    const int c = e / kStage, i = e - c * kStage;
+    if (i < min(s_ccnt[c], kStage) && s_gbase[c] + i < kListCap) ws.list[((size_t)b * C1 + c) * kListCap + s_gbase[c] + i] = s_stage[e];
   }
 }
 
@@ -431,7 +435,72 @@ k_class_fast_nms(const float* __restrict__ cls, int A, int C1, int top_k, float 
   auto slot_of = [&](int i) -> int { return full_scan ? i : s_cidx[i]; };
 
   // ---- stage 2: exact top-k by (score desc, anchor asc) ----------------------------------------
-  if (m > k) {
+  // Fast path (the usual case): ONE histogram pass over 256 linear bins of [min key, max key] finds the bin holding the k-th
+  // score; everything above it is in, the few elements of that bin are ranked exactly among themselves (score desc, anchor asc).
+  // The byte-wise radix select below needs 4+ passes whose first ones pile every key of a class onto two or three bins
+  // (shared-memory atomics on one address serialise); it stays as the fallback for heavy ties / the full-column scan.
+  bool selected = false;
+  if (m > k && !full_scan) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < m; i += kThreads) { const uint32_t v = s_ckey[i]; lo = min(lo, v); hi = max(hi, v); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { lo = min(lo, __shfl_xor_sync(kFull, lo, off)); hi = max(hi, __shfl_xor_sync(kFull, hi, off)); }
+    uint32_t* s_red = reinterpret_cast<uint32_t*>(s_area);            // [16] scratch (s_area is written only in stage 3)
+    if (lane == 0) { s_red[tid >> 5] = lo; s_red[8 + (tid >> 5)] = hi; }
+    for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
+    __syncthreads();
+    lo = s_red[0]; hi = s_red[8];
+#pragma unroll
+    for (int q = 1; q < kThreads / 32; ++q) { lo = min(lo, s_red[q]); hi = max(hi, s_red[8 + q]); }
+    const unsigned long long range = (unsigned long long)(hi - lo) + 1ull;
+    auto bin_of = [&](uint32_t v) -> int { return (int)((((unsigned long long)(v - lo)) << 8) / range); };
+    for (int i = tid; i < m; i += kThreads) atomicAdd(&s_hist[bin_of(s_ckey[i])], 1);
+    __syncthreads();
+    if (tid < 32) {                                                    // warp 0: bin of the k-th largest, count above it
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { loc[q] = s_hist[255 - (tid * 8 + q)]; sum += loc[q]; }
+      int incl = sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) { const int t2 = __shfl_up_sync(kFull, incl, off); if (tid >= off) incl += t2; }
+      const int excl = incl - sum;
+      if (excl < k && k <= incl) {
+        int run = excl;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (run + loc[q] >= k) { s_tmp[0] = 255 - (tid * 8 + q); s_tmp[1] = k - run; s_tmp[2] = loc[q]; break; }
+          run += loc[q];
+        }
+      }
+    }
+    __syncthreads();
+    const int bstar = s_tmp[0], need = s_tmp[1], e = s_tmp[2];
+    if (e <= kSortCap) {
+      unsigned long long* s_bkey = reinterpret_cast<unsigned long long*>(s_box);       // [256] boundary-bin elements (s_box is written in stage 3)
+      int* s_bslot = reinterpret_cast<int*>(s_bkey + kSortCap);                         // [256]
+      for (int i = tid; i < m; i += kThreads) {
+        const uint32_t key = s_ckey[i];
+        const int bn = bin_of(key);
+        if (bn < bstar) continue;
+        const int slot = s_cidx[i];
+        const unsigned long long comp = ((unsigned long long)(~key) << 32) | (uint32_t)canchor[slot];
+        if (bn > bstar) { const int pos = atomicAdd(&s_cnt, 1); s_sort[pos] = comp; s_slot[pos] = slot; }
+        else { const int q = atomicAdd(&s_m, 1); s_bkey[q] = comp; s_bslot[q] = slot; }
+      }
+      __syncthreads();
+      if (tid < e) {                                                   // exact rank inside the boundary bin (smaller composite = better)
+        const unsigned long long mine = s_bkey[tid];
+        int rank = 0;
+        for (int j = 0; j < e; ++j) rank += s_bkey[j] < mine ? 1 : 0;
+        if (rank < need) { const int pos = atomicAdd(&s_cnt, 1); s_sort[pos] = mine; s_slot[pos] = s_bslot[tid]; }
+      }
+      selected = true;
+    }
+    __syncthreads();
+  }
+  if (selected) {
+    // winners are in s_sort / s_slot
+  } else if (m > k) {
     SelectResult r = block_select_kth_largest(m, k, [&](int i, uint32_t& v) { v = key_of(i); return true; }, s_hist, s_tmp);
     uint32_t anchor_max = 0xFFFFFFFFu;   // take ties with anchor <= anchor_max
     if (r.cnt_eq > r.need_eq) {
