@@ -171,23 +171,3 @@ def test_detect_host_end_to_end(cuda):
     h2 = eng.detect_host(img2, p)
     for k in ('count', 'cls', 'anchor', 'score', 'box', 'coef'):
         assert np.array_equal(a[k], h[k]) and np.array_equal(b[k], h2[k]), k
-
-
-def test_training_branch_on_gpu_matches_reference_losses(cuda):
-    """Row a12 (first cut on torch autograd): the four losses on the GPU equal the reference's CPU goldens."""
-    from yolact_minimal_b200.config import make_config
-    from yolact_minimal_b200.modules.yolact import Yolact
-    g = load_golden('train.npz')
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    cfg = make_config('res50_coco', 128, mode='train', train_bs=2)
-    net = Yolact(cfg)
-    net.load_state_dict(ft.synth_state_dict('res50', seed=0, train=True), strict=True)
-    net = net.to(cuda).train()
-    img = torch.from_numpy(synth.image_batch(11, 2, 128)).to(cuda)
-    tg, mk = synth.train_targets(5, 2, 128)
-    losses = net(img, [torch.from_numpy(t).to(cuda) for t in tg], [torch.from_numpy(m).to(cuda) for m in mk])
-    got = np.asarray([float(l.detach()) for l in losses])
-    assert np.allclose(got, g['res50_S128_B2/losses'], rtol=2e-3), (got, g['res50_S128_B2/losses'])
-    sum(losses).backward()
-    assert net.backbone.conv1.weight.grad is not None and torch.isfinite(net.backbone.conv1.weight.grad).all()
