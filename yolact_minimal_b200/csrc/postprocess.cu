@@ -29,7 +29,7 @@ constexpr int kSortCap = 256;     // top_k, max_det <= 256
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kListCap = 2048;   // entries per (image, class) candidate list == the compact capacity of the per-class kernel
 constexpr int kBins = 116;        // sampled-score histogram: 8 bins per binary exponent over [2^-14, 1), + underflow / overflow
-constexpr int kSamples = 1024;    // sampled anchors per image (one thread each)
+constexpr int kSamples = 512;     // sampled anchors per image (one thread each)
 constexpr int kStage = 16;        // per-class staging slots of a phase-1 tile before one global append per class
 
 struct DetectWs {
@@ -285,84 +285,6 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
   for (int e = tid; e < C1 * kStage; e += kThreads) {
     const int c = e / kStage, i = e - c * kStage;
     if (i < min(s_ccnt[c], kStage) && s_gbase[c] + i < kListCap) ws.list[((size_t)b * C1 + c) * kListCap + s_gbase[c] + i] = s_stage[e];
-  }
-}
-
-// --------------------------------------------------------------------------------------------
-// phase 1, Fast-NMS path: streaming form.  One warp per chunk of 32 consecutive anchors, lanes over the class columns (81 = 3 per
-// lane): no shared-memory tile and no block barriers -- the tiled kernel above spends most of its time between its five
-// __syncthreads with only 4 blocks resident per SM.
-//   pass A   per anchor: 3 coalesced loads, warp max over the foreground columns -> candidate flag; per lane: how many of the
-//            chunk's candidates reach the class's cut (phase 0)
-//   reserve  ONE atomic for the chunk's candidate slots + at most 3 per lane for its class lists, all in flight together
-//   pass B   lane r decodes candidate r's box; the candidates' rows are re-read (L1 / L2 hits) and the passing scores written as
-//            (ordered key, slot) entries at the reserved list positions
-// --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_filter_decode_stream(const float* __restrict__ cls, const float* __restrict__ box, const float* __restrict__ anchors,
-                       int A, int C, float score_thr, int no_clip, DetectWs ws) {
-  const int b = blockIdx.y, lane = threadIdx.x & 31, C1 = C - 1;
-  const int a0 = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
-  if (a0 >= A) return;
-  const int na = min(32, A - a0);
-  uint32_t cutr[4];
-  int col[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    col[i] = lane + 32 * i;                                          // column of cls (0 = background); C <= 128
-    cutr[i] = (col[i] >= 1 && col[i] < C) ? ws.cut[(size_t)b * C1 + col[i] - 1] : 0xFFFFFFFFu;
-  }
-  const float* base_row = cls + ((size_t)b * A + a0) * C;
-  unsigned flags = 0u;
-  int cnt[4] = {0, 0, 0, 0};
-#pragma unroll 4
-  for (int r = 0; r < na; ++r) {
-    const float* row = base_row + (size_t)r * C;
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = col[i] < C ? __ldg(row + col[i]) : -INFINITY;       // (kept in L1 / L2 for pass B)
-    float m = -INFINITY; bool nan = false;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) if (col[i] >= 1 && col[i] < C) { nan |= (v[i] != v[i]); m = v[i] > m ? v[i] : m; }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { const float o = __shfl_xor_sync(kFull, m, off); m = o > m ? o : m; }
-    const bool keep = !__any_sync(kFull, nan) && m > score_thr;     // torch.max propagates NaN and NaN > thr is False (output_utils.py:140-143)
-    if (keep) {
-      flags |= 1u << r;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cnt[i] += float_to_ordered(v[i]) >= cutr[i] ? 1 : 0;
-    }
-  }
-  if (flags == 0u) return;                                            // warp-uniform
-  int sbase = 0;
-  if (lane == 0) sbase = atomicAdd(&ws.cand_count[b], __popc(flags));
-  int g[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) g[i] = cnt[i] ? atomicAdd(&ws.list_cnt[(size_t)b * C1 + col[i] - 1], cnt[i]) : 0;
-  sbase = __shfl_sync(kFull, sbase, 0);
-  if ((flags >> lane) & 1u) {                                         // lane r owns candidate r: slot, anchor index, decoded box
-    const int a = a0 + lane;
-    const size_t slot = (size_t)b * A + sbase + __popc(flags & ((1u << lane) - 1u));
-    ws.cand_anchor[slot] = a;
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(box) + (size_t)b * A + a);
-    const float4 an = __ldg(reinterpret_cast<const float4*>(anchors) + a);
-    ws.cand_box[slot] = decode_box(bb, an, no_clip);
-  }
-  unsigned rest = flags;
-  while (rest) {
-    const int r = __ffs(rest) - 1;
-    rest &= rest - 1;
-    const uint32_t slot = (uint32_t)(sbase + __popc(flags & ((1u << r) - 1u)));
-    const float* row = base_row + (size_t)r * C;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (col[i] < 1 || col[i] >= C) continue;
-      const uint32_t key = float_to_ordered(__ldg(row + col[i]));
-      if (key >= cutr[i]) {
-        const int pos = g[i]++;
-        if (pos < kListCap) ws.list[((size_t)b * C1 + col[i] - 1) * kListCap + pos] = make_uint2(key, slot);
-      }
-    }
   }
 }
 
@@ -949,14 +871,11 @@ extern "C" int yb_detect(const float* cls, const float* box, const float* coef, 
         k_sample_cuts<<<B, kSamples, hs, stream>>>(cls, A, C, p->score_thr, p->top_k, ws);
         YB_CHECK_LAUNCH();
       }
-      if (!getenv("YOLACT_B200_POST_TILED")) {
-        dim3 sgrid(ceil_div(A, 32 * (kThreads / 32)), B);
-        k_filter_decode_stream<<<sgrid, kThreads, 0, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
-      } else {                                                 // the tiled form (A/B tooling)
-        const size_t smem2 = smem + 8 + (size_t)C1 * kStage * sizeof(uint2);
-        YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        k_filter_decode<true><<<grid, kThreads, smem2, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
-      }
+      // (a warp-per-32-anchors streaming form without the shared-memory tile was tried and measured 45 % slower: too few loads
+      // in flight per warp; profiles/r2_postprocess_notes.txt)
+      const size_t smem2 = smem + 8 + (size_t)C1 * kStage * sizeof(uint2);
+      YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_filter_decode<true><<<grid, kThreads, smem2, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
     }
     YB_CHECK_LAUNCH();
   }
