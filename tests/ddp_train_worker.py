@@ -23,7 +23,7 @@ def main(out_path, arch='res50', S=128, per_rank=2, steps=6):
     torch.cuda.set_device(dev)
     net = tc.make_train_net(arch, S, per_rank, dev)
     ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=True)      # train.py:76
-    opt = torch.optim.SGD(ddp.parameters(), lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD(ddp.parameters(), lr=3e-4, momentum=0.9, weight_decay=5e-4)
     img = torch.from_numpy(synth.image_batch(20 + rank, per_rank, S)).to(dev)
     tg, mk = synth.train_targets(1 + rank, per_rank, S)
     tgt = [torch.from_numpy(t).to(dev) for t in tg]

@@ -118,20 +118,20 @@ def test_training_engine_vs_fp32_reference(cuda, arch, S, B):
 def test_sgd_steps_reduce_the_loss(cuda):
     from oracle import synth
     net = tc.make_train_net('res50', 128, 2, cuda)
-    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD(net.parameters(), lr=3e-4, momentum=0.9, weight_decay=5e-4)
     img = torch.from_numpy(synth.image_batch(11, 2, 128)).to(cuda)
     tg, mk = synth.train_targets(5, 2, 128)
     tgt = [torch.from_numpy(t).to(cuda) for t in tg]
     mks = [torch.from_numpy(m).to(cuda) for m in mk]
     hist = []
-    for _ in range(12):
+    for _ in range(8):
         losses = net(img, tgt, mks)
         total = sum(losses)
         opt.zero_grad()
         total.backward()
         opt.step()
-        hist.append(float(total))
-    assert all(np.isfinite(hist)) and hist[-1] < 0.8 * hist[0], hist
+        hist.append(float(total.detach()))
+    assert all(np.isfinite(hist)) and min(hist[4:]) < 0.6 * hist[0], hist        # (measured at lr 1e-3: 147 -> 118 -> 80 -> 62 -> 31 -> 23)
     # the engine keeps serving: eval forward after training uses the updated parameters and running statistics
     net.eval()
     with torch.no_grad():

@@ -28,7 +28,6 @@ constexpr int kThreads = 256;
 constexpr int kSortCap = 256;     // top_k, max_det <= 256
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kListCap = 2048;   // entries per (image, class) candidate list == the compact capacity of the per-class kernel
-constexpr int kBins = 116;        // sampled-score histogram: 8 bins per binary exponent over [2^-14, 1), + underflow / overflow
 constexpr int kSamples = 512;     // sampled anchors per image (one thread each)
 constexpr int kStage = 16;        // per-class staging slots of a phase-1 tile before one global append per class
 
@@ -46,8 +45,6 @@ struct DetectWs {
   uint32_t* cut;      // [B][C1]   ordered-key threshold below which a class score cannot reach the class's top_k (0 = take all)
   int* list_cnt;      // [B][C1]   entries appended (may exceed kListCap: the list overflowed -> exact fallback)
   uint2* list;        // [B][C1][kListCap]  (ordered score key, candidate slot)
-  int* hist;          // [B][C1][kBins]     sampled score histogram
-  int* samp;          // [B][2]    sampled candidate count, finished sample blocks
 };
 
 static size_t carve(DetectWs* w, char* base, int B, int A, int C1, int KC, bool traditional) {
@@ -65,8 +62,6 @@ static size_t carve(DetectWs* w, char* base, int B, int A, int C1, int KC, bool 
   w->cut = (uint32_t*)take(sizeof(uint32_t) * (size_t)B * C1);
   w->list_cnt = (int*)take(sizeof(int) * (size_t)B * C1);
   w->list = (uint2*)take(traditional ? 16 : sizeof(uint2) * (size_t)B * C1 * kListCap);
-  w->hist = (int*)take(traditional ? 16 : sizeof(int) * (size_t)B * C1 * kBins);
-  w->samp = (int*)take(sizeof(int) * (size_t)B * 2);
   return off;
 }
 
@@ -123,50 +118,57 @@ __device__ __forceinline__ float ovr_plus1(float4 a, float area_a, float4 b, flo
 // Only the top_k scores of a class row can matter (output_utils.py:12-14), so phase 1 appends an (anchor, class) score to the
 // class's candidate list only if it is >= a per-class cut -- instead of materialising the whole [C1][n] transposed score matrix
 // (2.6x the algorithmic DRAM traffic in round 1).  The cut comes from kSamples strided anchors: candidate samples are histogrammed
-// per class over ~12 % wide score bins; the cut is the lower edge of the bin where the sampled rank reaches ~3 top_k * (samples /
-// anchors).  Exactness does not depend on the estimate: the per-class kernel takes the list only if it holds >= top_k entries and
+// per class; the cut is the lower edge of the bin where the sampled rank reaches ~3 top_k * (samples / anchors).  Exactness does not depend on the estimate: the per-class kernel takes the list only if it holds >= top_k entries and
 // did not overflow (then the true top_k are all in it), otherwise it selects over the class column of `cls` itself.
+// The histogram is LINEAR over each class's own sampled [min, max] key range (256 bins): score distributions that sit inside one
+// binary octave (an untrained head: every class score ~ 1/81) still get a usable cut.
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ int score_bin(float f) {
-  if (!(f >= 6.103515625e-05f)) return 0;                 // < 2^-14, negative or NaN
-  if (f >= 1.f) return kBins - 1;
-  const uint32_t u = __float_as_uint(f);
-  const int e = (int)(u >> 23) - 127;                     // -14 .. -1
-  return 1 + (e + 14) * 8 + (int)((u >> 20) & 7u);
-}
-__device__ __forceinline__ float bin_lower_edge(int bin) {
-  if (bin <= 0) return 0.f;
-  if (bin >= kBins - 1) return 1.f;
-  const int q = bin - 1, e = q / 8 - 14, m = q & 7;
-  return __uint_as_float(((uint32_t)(e + 127) << 23) | ((uint32_t)m << 20));
-}
+constexpr int kCutBins = 256;
 
 __global__ void __launch_bounds__(kSamples)
 k_sample_cuts(const float* __restrict__ cls, int A, int C, float score_thr, int top_k, DetectWs ws) {
-  extern __shared__ int s_hist[];                         // [C1][kBins]
+  extern __shared__ int s_hist[];                         // [C1][kCutBins]
+  __shared__ uint32_t s_lo[128], s_hi[128];               // per-class range of the sampled candidates' score keys
   __shared__ int s_cnt;
   const int b = blockIdx.x, tid = threadIdx.x, C1 = C - 1;
-  for (int i = tid; i < C1 * kBins; i += kSamples) s_hist[i] = 0;
+  for (int i = tid; i < C1 * kCutBins; i += kSamples) s_hist[i] = 0;
+  for (int c = tid; c < C1; c += kSamples) { s_lo[c] = 0xFFFFFFFFu; s_hi[c] = 0u; }
   if (tid == 0) s_cnt = 0;
   __syncthreads();
   const long long a = ((long long)tid * A) / kSamples;    // strided anchors, one per thread
   const float* row = cls + ((size_t)b * A + (size_t)a) * C;
   float m = -INFINITY; bool has_nan = false;
   for (int c = 1; c < C; ++c) { const float v = __ldg(row + c); has_nan |= (v != v); m = v > m ? v : m; }
-  if (!has_nan && m > score_thr) {                        // a candidate (output_utils.py:140-143): histogram its class scores
+  const bool cand = !has_nan && m > score_thr;            // a candidate (output_utils.py:140-143)
+  if (cand) {
     atomicAdd(&s_cnt, 1);
-    for (int c = 1; c < C; ++c) atomicAdd(&s_hist[(c - 1) * kBins + score_bin(__ldg(row + c))], 1);
+    for (int i = 0; i < C1; ++i) {                        // classes rotated per thread: neighbouring threads hit different counters
+      const int c = (i + tid) % C1;
+      const uint32_t key = float_to_ordered(__ldg(row + c + 1));
+      atomicMin(&s_lo[c], key); atomicMax(&s_hi[c], key);
+    }
+  }
+  __syncthreads();
+  if (cand) {
+    for (int i = 0; i < C1; ++i) {
+      const int c = (i + tid) % C1;
+      const uint32_t key = float_to_ordered(__ldg(row + c + 1)), lo = s_lo[c];
+      const unsigned long long range = (unsigned long long)(s_hi[c] - lo) + 1ull;
+      atomicAdd(&s_hist[c * kCutBins + (int)((((unsigned long long)(key - lo)) << 8) / range)], 1);
+    }
   }
   __syncthreads();
   const double est_n = (double)s_cnt * A / kSamples;      // estimated number of candidates of the image
   for (int c = tid; c < C1; c += kSamples) {
     uint32_t cut = 0u;
     if (est_n > 0.6 * kListCap) {                         // otherwise every candidate fits the list: take all
-      const int want = (int)(3.0 * top_k * kSamples / A) + 8;      // sampled rank of ~3 top_k survivors, + margin
+      const int want = (int)(3.0 * top_k * kSamples / A) + 6;      // sampled rank of ~3 top_k survivors, + margin
+      const uint32_t lo = s_lo[c];
+      const unsigned long long range = (unsigned long long)(s_hi[c] - lo) + 1ull;
       int acc = 0;
-      for (int bin = kBins - 1; bin > 0; --bin) {
-        acc += s_hist[c * kBins + bin];
-        if (acc >= want) { cut = float_to_ordered(bin_lower_edge(bin)); break; }
+      for (int bin = kCutBins - 1; bin > 0; --bin) {
+        acc += s_hist[c * kCutBins + bin];
+        if (acc >= want) { cut = lo + (uint32_t)(((unsigned long long)bin * range + 255ull) >> 8); break; }   // smallest key of that bin
       }
     }
     ws.cut[(size_t)b * C1 + c] = cut;
@@ -862,11 +864,10 @@ extern "C" int yb_detect(const float* cls, const float* box, const float* coef, 
       YB_CHECK_CUDA(cudaFuncSetAttribute(k_filter_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_filter_decode<false><<<grid, kThreads, smem, stream>>>(cls, box, anchors, A, C, p->score_thr, p->no_clip, ws);
     } else {
-      // cut [B][C1] | list_cnt [B][C1] are adjacent 256-byte aligned blocks: zero them (cut 0 = take all) and the sample state
+      // cut [B][C1] | list_cnt [B][C1] are adjacent 256-byte aligned blocks: zero them (cut 0 = take all)
       YB_CHECK_CUDA(cudaMemsetAsync(ws.cut, 0, (size_t)((char*)ws.list - (char*)ws.cut), stream));
-      YB_CHECK_CUDA(cudaMemsetAsync(ws.samp, 0, sizeof(int) * (size_t)B * 2, stream));
       if (A > kListCap) {                                     // small heads: every candidate fits its list, no sampling
-        const size_t hs = (size_t)C1 * kBins * sizeof(int);
+        const size_t hs = (size_t)C1 * kCutBins * sizeof(int);
         YB_CHECK_CUDA(cudaFuncSetAttribute(k_sample_cuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
         k_sample_cuts<<<B, kSamples, hs, stream>>>(cls, A, C, p->score_thr, p->top_k, ws);
         YB_CHECK_LAUNCH();
