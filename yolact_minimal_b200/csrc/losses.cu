@@ -8,7 +8,7 @@
 // gradient w.r.t. each network output is produced in the same pass as the loss.  fp32 throughout; the float operations that
 // decide a LABEL (IoU, thresholds) are separately rounded in the reference's order (no FMA contraction) so that labels and
 // matched indices equal the reference's bit for bit.
-#include "common.cuh"
+#include "train.cuh"
 
 #include <math.h>
 #include <stdint.h>
@@ -16,7 +16,7 @@
 namespace yb {
 namespace {
 
-constexpr int kMaxGt = 256;              // ground-truth instances per image held in shared memory
+constexpr int kMaxGt = kLossMaxGt;       // ground-truth instances per image held in shared memory
 
 struct LossWs {                          // carved out of the caller's workspace
   float* best_iou;        // [B,A]
@@ -295,21 +295,24 @@ __device__ __forceinline__ float bilinear_at(const float* __restrict__ m, int S,
   return ly0 * (lx0 * m[(size_t)y0 * S + x0] + lx1 * m[(size_t)y0 * S + x1]) + ly1 * (lx0 * m[(size_t)y1 * S + x0] + lx1 * m[(size_t)y1 * S + x1]);
 }
 
-__global__ void __launch_bounds__(256) k_downsample_masks(const float* __restrict__ masks, int S, int P, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_downsample_masks(const float* __restrict__ masks, const int32_t* __restrict__ gt_off, int B, int S, int P,
+                                                          uint8_t* __restrict__ out) {
   const int j = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= P * P) return;
+  if (i >= P * P || j >= gt_off[B]) return;                  // (the grid may be sized for a capacity: CUDA-graph replay)
   out[(size_t)j * P * P + i] = bilinear_at(masks + (size_t)j * S * S, S, P, i / P, i % P) > 0.5f ? 1 : 0;
 }
 
 // ---- positives of an image, in anchor order; more than `limit` -> a uniformly random subset of `limit` (yolact.py:261-268) ----
 __device__ __forceinline__ uint32_t hash32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
 
-__global__ void __launch_bounds__(1024) k_mask_select(const int32_t* __restrict__ labels, int A, int limit, uint32_t seed, uint32_t* __restrict__ keys_ws /*[B,A]*/,
+__global__ void __launch_bounds__(1024) k_mask_select(const int32_t* __restrict__ labels, int A, int limit, uint32_t seed_value, const uint32_t* __restrict__ seed_dev,
+                                                      uint32_t* __restrict__ keys_ws /*[B,A]*/,
                                                       int32_t* __restrict__ sel, int32_t* __restrict__ sel_count, int B) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t bc[2];
   __shared__ int scan[1024];
   const int b = blockIdx.x;
+  const uint32_t seed = seed_dev ? *seed_dev : seed_value;
   const int32_t* lab = labels + (size_t)b * A;
   uint32_t* keys = keys_ws + (size_t)b * A;
   const int per = (A + blockDim.x - 1) / blockDim.x, a0 = threadIdx.x * per, a1 = min(a0 + per, A);
@@ -514,11 +517,14 @@ extern "C" size_t yb_losses_workspace_bytes(const yb_loss_params* p, int total_g
   return carve(&w, nullptr, *p, total_gt);
 }
 
-extern "C" int yb_losses(const yb_loss_params* p, const float* cls, const float* box, const float* coef, const float* proto, const float* seg, int ld_seg,
-                         const float* anchors, const float* gt, const int32_t* gt_offset, const float* gt_masks, int total_gt, int max_gt_per_image,
-                         uint32_t seed, const float* grad_scale, float* losses, float* d_cls, float* d_box, float* d_coef, float* d_proto, float* d_seg,
-                         int32_t* dbg_labels, int32_t* dbg_matched_idx, float* dbg_offsets, uint8_t* dbg_neg, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+namespace yb {
+// total_gt / max_gt_per_image only size grids and the workspace (the kernels read the real counts from gt_offset), so a caller that
+// replays this launch sequence from a CUDA graph passes CAPACITIES here and the seed through device memory (seed_dev).
+int losses_impl(const yb_loss_params* p, const float* cls, const float* box, const float* coef, const float* proto, const float* seg, int ld_seg,
+                const float* anchors, const float* gt, const int32_t* gt_offset, const float* gt_masks, int total_gt, int max_gt_per_image,
+                uint32_t seed, const uint32_t* seed_dev, const float* grad_scale, float* losses, float* d_cls, float* d_box, float* d_coef, float* d_proto,
+                float* d_seg, int32_t* dbg_labels, int32_t* dbg_matched_idx, float* dbg_offsets, uint8_t* dbg_neg, void* workspace, size_t workspace_bytes,
+                void* stream) {
   YB_REQUIRE(p && cls && box && coef && proto && seg && anchors && gt && gt_offset && gt_masks && losses && workspace, YB_ERR_INVALID, "yb_losses: NULL argument");
   YB_REQUIRE(p->batch >= 1 && p->num_anchors >= 1 && p->num_classes >= 2 && p->num_classes <= 129, YB_ERR_INVALID, "yb_losses: batch=%d anchors=%d classes=%d",
              p->batch, p->num_anchors, p->num_classes);
@@ -555,11 +561,11 @@ extern "C" int yb_losses(const yb_loss_params* p, const float* cls, const float*
                                                             p->bbox_alpha, w.acc, d_cls, d_box);
   YB_CHECK_LAUNCH();
   if (total_gt > 0) {
-    k_downsample_masks<<<dim3(ceil_div(P * P, 256), total_gt), 256, 0, s>>>(gt_masks, S, P, w.ds_mask);
+    k_downsample_masks<<<dim3(ceil_div(P * P, 256), total_gt), 256, 0, s>>>(gt_masks, gt_offset, B, S, P, w.ds_mask);
     YB_CHECK_LAUNCH();
   }
   // the OHEM mark buffer is free again: reuse it for the random subset keys
-  k_mask_select<<<B, 1024, 0, s>>>(w.labels, A, p->masks_to_train, seed, reinterpret_cast<uint32_t*>(w.mark), w.sel, w.sel_count, B);
+  k_mask_select<<<B, 1024, 0, s>>>(w.labels, A, p->masks_to_train, seed, seed_dev, reinterpret_cast<uint32_t*>(w.mark), w.sel, w.sel_count, B);
   YB_CHECK_LAUNCH();
   if (d_coef) YB_CHECK_CUDA(cudaMemsetAsync(d_coef, 0, (size_t)rows * K * 4, s));
   {
@@ -578,4 +584,14 @@ extern "C" int yb_losses(const yb_loss_params* p, const float* cls, const float*
     YB_CHECK_LAUNCH();
   }
   return YB_OK;
+}
+}  // namespace yb
+
+extern "C" int yb_losses(const yb_loss_params* p, const float* cls, const float* box, const float* coef, const float* proto, const float* seg, int ld_seg,
+                         const float* anchors, const float* gt, const int32_t* gt_offset, const float* gt_masks, int total_gt, int max_gt_per_image,
+                         uint32_t seed, const float* grad_scale, float* losses, float* d_cls, float* d_box, float* d_coef, float* d_proto, float* d_seg,
+                         int32_t* dbg_labels, int32_t* dbg_matched_idx, float* dbg_offsets, uint8_t* dbg_neg, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return yb::losses_impl(p, cls, box, coef, proto, seg, ld_seg, anchors, gt, gt_offset, gt_masks, total_gt, max_gt_per_image, seed, nullptr, grad_scale, losses,
+                         d_cls, d_box, d_coef, d_proto, d_seg, dbg_labels, dbg_matched_idx, dbg_offsets, dbg_neg, workspace, workspace_bytes, stream);
 }

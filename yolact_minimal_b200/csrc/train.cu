@@ -96,11 +96,18 @@ struct yb_train {
   int ld_seg = 0;
   void* loss_ws = nullptr; size_t loss_ws_bytes = 0;
   // per-step state read by the closures
-  const float* cur_gt = nullptr; const int32_t* cur_gt_off = nullptr; const float* cur_masks = nullptr;
-  int cur_total_gt = 0, cur_max_gt = 0; uint32_t cur_seed = 0; float* cur_losses = nullptr;
+  const float* cur_gt = nullptr;
   yb_train_hparams hp{};
-  const float* loss_grad = nullptr;                                // device, 4 floats (NULL = ones)
   float* d_losses_scratch = nullptr;
+  // graph-stable copies of the per-step inputs, and the captured forward / backward launch lists
+  float* p_gt = nullptr; int32_t* p_gt_off = nullptr; float* p_masks = nullptr; int mask_cap = 0;
+  float *p_loss_grad = nullptr, *p_losses = nullptr; uint32_t* p_seed = nullptr;
+  uint32_t seed_host = 0;
+  cudaGraphExec_t g_fwd = nullptr, g_bwd = nullptr;
+  cudaStream_t gstream = nullptr;                                     // the graphs are captured and replayed here (the caller's stream may be the
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;                      // legacy default stream, which cannot be captured), fenced by two events
+  bool use_graphs = true;
+  yb_train_hparams g_hp{};
   uint64_t launches_fwd = 0, launches_bwd = 0;
 
   int add_bound(const std::string& n, int64_t count, int kind) {
@@ -773,9 +780,15 @@ extern "C" int yb_train_create(const yb_net_config* cfg, int batch, int precisio
 
 extern "C" void yb_train_destroy(yb_train* t) {
   if (!t) return;
+  if (t->g_fwd) cudaGraphExecDestroy(t->g_fwd);
+  if (t->g_bwd) cudaGraphExecDestroy(t->g_bwd);
+  if (t->ev_in) cudaEventDestroy(t->ev_in);
+  if (t->ev_out) cudaEventDestroy(t->ev_out);
+  if (t->gstream) cudaStreamDestroy(t->gstream);
   for (TcPlan* p : t->plans) tc_plan_destroy(p);
   for (void* p : t->allocs) cudaFree(p);
   if (t->loss_ws) cudaFree(t->loss_ws);
+  if (t->p_masks) cudaFree(t->p_masks);
   delete t;
 }
 
@@ -808,24 +821,117 @@ extern "C" int yb_train_set_anchors(yb_train* t, const float* anchors_host, int 
 }
 
 namespace {
-int run_losses(yb_train* t, bool with_grads, cudaStream_t s) {
+void drop_graphs(yb_train* t) {
+  if (t->g_fwd) cudaGraphExecDestroy(t->g_fwd);
+  if (t->g_bwd) cudaGraphExecDestroy(t->g_bwd);
+  t->g_fwd = t->g_bwd = nullptr;
+}
+
+yb_loss_params loss_params(const yb_train* t) {
   yb_loss_params p; memset(&p, 0, sizeof(p));
   p.batch = t->B; p.num_anchors = t->A; p.num_classes = t->cfg.num_classes; p.coef_dim = t->cfg.coef_dim; p.proto_size = t->P; p.seg_size = t->Hs;
   p.mask_size = t->S; p.pos_iou_thr = t->hp.pos_iou_thr; p.neg_iou_thr = t->hp.neg_iou_thr; p.neg_pos_ratio = t->hp.neg_pos_ratio;
   p.masks_to_train = t->hp.masks_to_train; p.conf_alpha = t->hp.conf_alpha; p.bbox_alpha = t->hp.bbox_alpha; p.mask_alpha = t->hp.mask_alpha;
   p.semantic_alpha = t->hp.semantic_alpha;
-  const size_t need = yb_losses_workspace_bytes(&p, t->cur_total_gt);
-  if (need > t->loss_ws_bytes) {
-    YB_CHECK_CUDA(cudaStreamSynchronize(s));
-    if (t->loss_ws) cudaFree(t->loss_ws);
-    t->loss_ws = nullptr; t->loss_ws_bytes = 0;
-    YB_CHECK_CUDA(cudaMalloc(&t->loss_ws, need * 2));
-    t->loss_ws_bytes = need * 2;
+  return p;
+}
+
+// grids and workspace are sized for the CAPACITY of the target buffers (the kernels read the real counts from p_gt_off), so the
+// same launch sequence can be replayed from a CUDA graph whatever the step's ground truth is
+int run_losses(yb_train* t, bool with_grads, cudaStream_t s) {
+  const yb_loss_params p = loss_params(t);
+  return losses_impl(&p, t->cls, t->box, t->coef, t->proto, t->seg, t->ld_seg, t->d_anchors, t->p_gt, t->p_gt_off, t->p_masks, t->mask_cap, kLossMaxGt, 0,
+                     t->p_seed, with_grads ? t->p_loss_grad : nullptr, with_grads ? t->d_losses_scratch : t->p_losses, with_grads ? t->g_cls : nullptr,
+                     with_grads ? t->g_box : nullptr, with_grads ? t->g_coef : nullptr, with_grads ? t->g_proto : nullptr, with_grads ? t->g_seg : nullptr,
+                     nullptr, nullptr, nullptr, nullptr, t->loss_ws, t->loss_ws_bytes, s);
+}
+
+int ensure_target_capacity(yb_train* t, int total_gt, cudaStream_t s) {
+  if (!t->p_gt) {
+    YB_PROPAGATE(dev_alloc(t, (void**)&t->p_gt, (size_t)t->B * kLossMaxGt * 5 * 4));
+    YB_PROPAGATE(dev_alloc(t, (void**)&t->p_gt_off, (size_t)(t->B + 1) * 4));
+    YB_PROPAGATE(dev_alloc(t, (void**)&t->p_loss_grad, 16)); YB_PROPAGATE(dev_alloc(t, (void**)&t->p_losses, 16)); YB_PROPAGATE(dev_alloc(t, (void**)&t->p_seed, 16));
   }
-  return yb_losses(&p, t->cls, t->box, t->coef, t->proto, t->seg, t->ld_seg, t->d_anchors, t->cur_gt, t->cur_gt_off, t->cur_masks, t->cur_total_gt,
-                   t->cur_max_gt, t->cur_seed, t->loss_grad, with_grads ? t->d_losses_scratch : t->cur_losses, with_grads ? t->g_cls : nullptr,
-                   with_grads ? t->g_box : nullptr, with_grads ? t->g_coef : nullptr, with_grads ? t->g_proto : nullptr, with_grads ? t->g_seg : nullptr,
-                   nullptr, nullptr, nullptr, nullptr, t->loss_ws, t->loss_ws_bytes, s);
+  if (total_gt > t->mask_cap) {
+    YB_CHECK_CUDA(cudaStreamSynchronize(s));
+    drop_graphs(t);
+    if (t->p_masks) cudaFree(t->p_masks);
+    if (t->loss_ws) cudaFree(t->loss_ws);
+    t->p_masks = nullptr; t->loss_ws = nullptr;
+    t->mask_cap = total_gt < 16 ? 32 : 2 * total_gt;
+    YB_CHECK_CUDA(cudaMalloc(&t->p_masks, (size_t)t->mask_cap * t->S * t->S * 4));
+    const yb_loss_params p = loss_params(t);
+    t->loss_ws_bytes = yb_losses_workspace_bytes(&p, t->mask_cap);
+    YB_CHECK_CUDA(cudaMalloc(&t->loss_ws, t->loss_ws_bytes));
+  }
+  return YB_OK;
+}
+
+int forward_list(yb_train* t, cudaStream_t s) {
+  static const bool dbg = getenv("YOLACT_B200_TRAIN_DEBUG") != nullptr;
+  YB_CHECK_CUDA(cudaMemsetAsync(t->stats, 0, t->stats_floats * 4, s));
+  YB_PROPAGATE(launch_pack_weights(t->d_pack, (int)t->pack_descs.size(), t->dt, s));
+  for (size_t i = 0; i < t->fwd.size(); ++i) {
+    YB_PROPAGATE(t->fwd[i](s));
+    if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: forward launch %zu (%s): %s", i, t->fwd_what[i].c_str(), cudaGetErrorString(e)); }
+  }
+  YB_PROPAGATE(run_losses(t, false, s));
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: losses: %s", cudaGetErrorString(e)); }
+  return YB_OK;
+}
+
+int backward_list(yb_train* t, cudaStream_t s) {
+  static const bool dbg = getenv("YOLACT_B200_TRAIN_DEBUG") != nullptr;
+  YB_CHECK_CUDA(cudaMemsetAsync(t->stats, 0, t->stats_floats * 4, s));    // BN reductions / bias sums of this pass start from zero
+  YB_PROPAGATE(run_losses(t, true, s));
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: loss gradients: %s", cudaGetErrorString(e)); }
+  for (size_t i = 0; i < t->bwd.size(); ++i) {
+    YB_PROPAGATE(t->bwd[i](s));
+    if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: backward launch %zu (%s): %s", i, t->bwd_what[i].c_str(), cudaGetErrorString(e)); }
+  }
+  for (auto& f : t->bwd_tail) YB_PROPAGATE(f(s));
+  YB_PROPAGATE(launch_unpack_wgrad(t->d_unpack, (int)t->unpack_descs.size(), s));
+  return YB_OK;
+}
+
+// replay `list` from a CUDA graph (captured on first use) on the engine's own stream, ordered after / before the caller's stream by
+// events; any capture problem falls back to plain launches on the caller's stream for good
+int run_graphed(yb_train* t, cudaGraphExec_t* exec, int (*list)(yb_train*, cudaStream_t), cudaStream_t s, uint64_t* launches) {
+  static const bool off = getenv("YOLACT_B200_TRAIN_NO_GRAPH") != nullptr || getenv("YOLACT_B200_TRAIN_DEBUG") != nullptr;
+  const uint64_t l0 = yb_launch_count();
+  if (off || !t->use_graphs) { const int st = list(t, s); *launches = yb_launch_count() - l0; return st; }
+  if (!t->gstream) {
+    if (cudaStreamCreateWithFlags(&t->gstream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&t->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError(); t->use_graphs = false;
+      return run_graphed(t, exec, list, s, launches);
+    }
+  }
+  YB_CHECK_CUDA(cudaEventRecord(t->ev_in, s));
+  YB_CHECK_CUDA(cudaStreamWaitEvent(t->gstream, t->ev_in, 0));
+  if (!*exec) {
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(t->gstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int st = YB_OK;
+    if (ok) {
+      st = list(t, t->gstream);
+      ok = cudaStreamEndCapture(t->gstream, &graph) == cudaSuccess && st == YB_OK && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      *exec = nullptr; t->use_graphs = false;
+      if (st != YB_OK) return st;
+      return run_graphed(t, exec, list, s, launches);             // plain launches on the caller's stream
+    }
+    *launches = yb_launch_count() - l0;                            // kernels per replay
+  }
+  YB_CHECK_CUDA(cudaGraphLaunch(*exec, t->gstream));
+  count_launch(*launches);
+  YB_CHECK_CUDA(cudaEventRecord(t->ev_out, t->gstream));
+  YB_CHECK_CUDA(cudaStreamWaitEvent(s, t->ev_out, 0));
+  return YB_OK;
 }
 }  // namespace
 
@@ -836,23 +942,21 @@ extern "C" int yb_train_forward(yb_train* t, const float* img, const float* gt, 
   for (const auto& b : t->bound) YB_REQUIRE(b.data != nullptr, YB_ERR_STATE, "yb_train_forward: tensor '%s' was never bound", b.name.c_str());
   YB_REQUIRE(hp->masks_to_train >= 1 && hp->neg_pos_ratio >= 1, YB_ERR_INVALID, "yb_train_forward: hparams");
   cudaStream_t s = (cudaStream_t)stream;
+  YB_REQUIRE(total_gt >= 1 && total_gt <= t->B * kLossMaxGt && max_gt_per_image <= kLossMaxGt, YB_ERR_UNSUPPORTED,
+             "yb_train_forward: %d ground-truth instances (max %d per image)", total_gt, kLossMaxGt);
+  if (memcmp(&t->g_hp, hp, sizeof(*hp)) != 0) { drop_graphs(t); t->g_hp = *hp; }       // hyper-parameters are baked into the captured launches
   t->hp = *hp;
-  t->cur_gt = gt; t->cur_gt_off = gt_offset; t->cur_masks = gt_masks; t->cur_total_gt = total_gt; t->cur_max_gt = max_gt_per_image; t->cur_seed = seed;
-  t->cur_losses = losses;
-  if (t->descs_dirty) { YB_PROPAGATE(resolve_descs(t)); t->descs_dirty = false; }
-  const uint64_t l0 = yb_launch_count();
+  if (t->descs_dirty) { YB_PROPAGATE(resolve_descs(t)); t->descs_dirty = false; drop_graphs(t); }   // so are the bound pointers
+  YB_PROPAGATE(ensure_target_capacity(t, total_gt, s));
+  t->cur_gt = gt;                                                    // (marks "forward was called"; the kernels read the copies below)
+  t->seed_host = seed;
   YB_CHECK_CUDA(cudaMemcpyAsync(t->d_img, img, (size_t)t->B * 3 * t->S * t->S * 4, cudaMemcpyDeviceToDevice, s));
-  YB_CHECK_CUDA(cudaMemsetAsync(t->stats, 0, t->stats_floats * 4, s));
-  YB_PROPAGATE(launch_pack_weights(t->d_pack, (int)t->pack_descs.size(), t->dt, s));
-  static const bool dbg = getenv("YOLACT_B200_TRAIN_DEBUG") != nullptr;
-  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: before the forward list: %s", cudaGetErrorString(e)); }
-  for (size_t i = 0; i < t->fwd.size(); ++i) {
-    YB_PROPAGATE(t->fwd[i](s));
-    if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: forward launch %zu (%s): %s", i, t->fwd_what[i].c_str(), cudaGetErrorString(e)); }
-  }
-  YB_PROPAGATE(run_losses(t, false, s));
-  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: losses: %s", cudaGetErrorString(e)); }
-  t->launches_fwd = yb_launch_count() - l0;
+  YB_CHECK_CUDA(cudaMemcpyAsync(t->p_gt, gt, (size_t)total_gt * 5 * 4, cudaMemcpyDeviceToDevice, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(t->p_gt_off, gt_offset, (size_t)(t->B + 1) * 4, cudaMemcpyDeviceToDevice, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(t->p_masks, gt_masks, (size_t)total_gt * t->S * t->S * 4, cudaMemcpyDeviceToDevice, s));
+  YB_CHECK_CUDA(cudaMemcpyAsync(t->p_seed, &t->seed_host, 4, cudaMemcpyHostToDevice, s));
+  YB_PROPAGATE(run_graphed(t, &t->g_fwd, forward_list, s, &t->launches_fwd));
+  YB_CHECK_CUDA(cudaMemcpyAsync(losses, t->p_losses, 16, cudaMemcpyDeviceToDevice, s));
   return YB_OK;
 }
 
@@ -860,20 +964,9 @@ extern "C" int yb_train_backward(yb_train* t, const float* loss_grad, void* stre
   YB_REQUIRE(t, YB_ERR_INVALID, "yb_train_backward: NULL argument");
   YB_REQUIRE(t->cur_gt != nullptr, YB_ERR_STATE, "yb_train_backward: call yb_train_forward first");
   cudaStream_t s = (cudaStream_t)stream;
-  t->loss_grad = loss_grad;
-  const uint64_t l0 = yb_launch_count();
-  YB_CHECK_CUDA(cudaMemsetAsync(t->stats, 0, t->stats_floats * 4, s));    // BN reductions / bias sums of this pass start from zero
-  static const bool dbg = getenv("YOLACT_B200_TRAIN_DEBUG") != nullptr;
-  YB_PROPAGATE(run_losses(t, true, s));
-  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: loss gradients: %s", cudaGetErrorString(e)); }
-  for (size_t i = 0; i < t->bwd.size(); ++i) {
-    YB_PROPAGATE(t->bwd[i](s));
-    if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: backward launch %zu (%s): %s", i, t->bwd_what[i].c_str(), cudaGetErrorString(e)); }
-  }
-  for (auto& f : t->bwd_tail) YB_PROPAGATE(f(s));
-  if (dbg) { cudaError_t e = cudaStreamSynchronize(s); YB_REQUIRE(e == cudaSuccess, YB_ERR_CUDA, "train debug: backward tail: %s", cudaGetErrorString(e)); }
-  YB_PROPAGATE(launch_unpack_wgrad(t->d_unpack, (int)t->unpack_descs.size(), s));
-  t->launches_bwd = yb_launch_count() - l0;
+  if (loss_grad) YB_CHECK_CUDA(cudaMemcpyAsync(t->p_loss_grad, loss_grad, 16, cudaMemcpyDeviceToDevice, s));
+  else { const float one[4] = {1.f, 1.f, 1.f, 1.f}; YB_CHECK_CUDA(cudaMemcpyAsync(t->p_loss_grad, one, 16, cudaMemcpyHostToDevice, s)); }
+  YB_PROPAGATE(run_graphed(t, &t->g_bwd, backward_list, s, &t->launches_bwd));
   return YB_OK;
 }
 

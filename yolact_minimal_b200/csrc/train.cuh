@@ -51,4 +51,13 @@ int launch_head_grad(const float* dcls, const float* dbox, const float* dcoef, c
                      int anchor_offset, int A_total, int ldo, void* out, cudaStream_t s);
 int launch_scale_copy(const float* src, float* dst, int n, float scale, cudaStream_t s);
 
+
+// losses.cu: yb_losses with the seed in device memory; total_gt / max_gt_per_image only size grids and the workspace (graph replay)
+constexpr int kLossMaxGt = 256;
+int losses_impl(const yb_loss_params* p, const float* cls, const float* box, const float* coef, const float* proto, const float* seg, int ld_seg,
+                const float* anchors, const float* gt, const int32_t* gt_offset, const float* gt_masks, int total_gt, int max_gt_per_image,
+                uint32_t seed, const uint32_t* seed_dev, const float* grad_scale, float* losses, float* d_cls, float* d_box, float* d_coef, float* d_proto,
+                float* d_seg, int32_t* dbg_labels, int32_t* dbg_matched_idx, float* dbg_offsets, uint8_t* dbg_neg, void* workspace, size_t workspace_bytes,
+                void* stream);
+
 }  // namespace yb

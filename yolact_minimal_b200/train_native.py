@@ -145,8 +145,16 @@ def training_step(net, img, box_classes, masks_gt):
     eng = engines.get(key)
     if eng is None:
         eng = engines[key] = TrainEngine(net, B, precision)
-    tensors = dict(net.named_parameters())
-    tensors.update(dict(net.named_buffers()))
+    cache = net.__dict__.get('_train_tensor_cache')
+    if cache is None or any(t is not u for (_, t), u in zip(cache[1], cache[2]())):        # a parameter / buffer object was replaced
+        tensors = dict(net.named_parameters())
+        tensors.update(dict(net.named_buffers()))
+        objs = [(n, tensors[n]) for n, _, _ in eng.names]
+        holders = [(net.get_submodule(n.rsplit('.', 1)[0]) if '.' in n else net, n.rsplit('.', 1)[-1]) for n, _, _ in eng.names]
+        getter = lambda: [m._parameters[a] if a in m._parameters else m._buffers[a] for m, a in holders]
+        bns = [b for n, b in net.named_buffers() if n.endswith('num_batches_tracked')]
+        cache = net.__dict__['_train_tensor_cache'] = (tensors, objs, getter, bns)
+    tensors = cache[0]
     eng.bind(tensors)
     eng._params = [tensors[n] for n in eng.param_names]
     dev = img.device
@@ -159,7 +167,6 @@ def training_step(net, img, box_classes, masks_gt):
     seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())             # host RNG (like the reference's torch.randperm, yolact.py:263)
     losses = _NativeTrainStep.apply(eng, img.detach().to(torch.float32).contiguous(), gt, gt_off, masks, int(gt.shape[0]), max(counts), seed,
                                     *eng._params)
-    bns = [b for n, b in net.named_buffers() if n.endswith('num_batches_tracked')]
-    if bns:
-        torch._foreach_add_(bns, 1)
+    if cache[3]:
+        torch._foreach_add_(cache[3], 1)
     return tuple(losses.unbind(0))
