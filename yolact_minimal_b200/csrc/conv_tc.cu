@@ -77,6 +77,8 @@ struct TcParams {
   int gemm_ntile_tap;     // N tiles per tap
   int gemm_shift[16];     // per-tap column shift of the B operand
   int accumulate;         // out_mode 2: out += result (shared weights: one launch per use)
+  int gemm_splits;        // split-K: the K range of every output tile is cut into gemm_splits pieces of gemm_kb_split k-blocks, one
+  int gemm_kb_split;      // scheduling unit each; the partial tiles are added to `out` with atomics (out is zeroed by the caller)
   Geom g;
   const float* bias;
   const void* residual;
@@ -276,9 +278,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
     float* o = (float*)p.out + m * p.Cout_pad + col;
 #pragma unroll
     for (int i = 0; i < NCOL; i += 4) {
-      float4 r = make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]), __uint_as_float(acc[i + 3]));
-      if (p.accumulate) { const float4 q = *reinterpret_cast<const float4*>(o + i); r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
-      *reinterpret_cast<float4*>(o + i) = r;
+      const float4 r = make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]), __uint_as_float(acc[i + 3]));
+      if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(o + i), r);         // split-K partial tiles / shared weights: 128-bit reduction
+      else *reinterpret_cast<float4*>(o + i) = r;
     }
     return;
   }
@@ -346,13 +348,23 @@ __device__ __forceinline__ bool tile_at(const TcParams& p, int i, int& m_tile, i
     m_tile = unit / p.n_tiles + i * (units / p.n_tiles);
     if (m_tile >= p.m_tiles) return false;
   } else {
-    const int tile = unit + i * units;
-    if (tile >= p.m_tiles * p.n_tiles) return false;
+    int tile = unit + i * units;
+    if (p.gemm) {                                                  // split-K: the split index is recovered by gemm_split_at()
+      if (tile >= p.m_tiles * p.n_tiles * p.gemm_splits) return false;
+      tile %= p.m_tiles * p.n_tiles;
+    } else if (tile >= p.m_tiles * p.n_tiles) return false;
     m_tile = tile / p.n_tiles;
     n_tile = tile - m_tile * p.n_tiles;
   }
   if (PAIR) m_tile = 2 * m_tile + (int)cluster_ctarank();
   return true;
+}
+
+// split-K GEMM: k-block range [kb0, kb1) of CTA-local iteration i
+__device__ __forceinline__ void gemm_kb_range(const TcParams& p, int i, int& kb0, int& kb1) {
+  const int split = ((int)blockIdx.x + i * (int)gridDim.x) / (p.m_tiles * p.n_tiles);
+  kb0 = split * p.gemm_kb_split;
+  kb1 = min(kb0 + p.gemm_kb_split, p.kb_per_tap);
 }
 
 template <bool F16, bool PAIR>
@@ -489,9 +501,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           n0 = (n_tile - tap * p.gemm_ntile_tap) * p.BN;
           bcol0 = p.gemm_shift[tap];
         }
+        int kb_lo = 0, kb_hi = p.kb_per_tap;
+        if (p.gemm) gemm_kb_range(p, i, kb_lo, kb_hi);
         for (int t = 0; t < p.ntaps; ++t) {
           const int row = m0 + p.tap_shift[t];
-          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             if (PAIR) {
               const uint32_t full_addr = map_to_rank(smem_u32(&full[stage]), 0);
@@ -565,7 +579,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
         }
-        for (int kb = 0; kb < num_kb && !p.slab; ++kb) {
+        int kb_lo = 0, kb_hi = num_kb;
+        if (p.gemm) gemm_kb_range(p, i, kb_lo, kb_hi);
+        for (int kb = kb_lo; kb < kb_hi && !p.slab; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
@@ -576,8 +592,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)k * bstep, idesc_k, (kb | k) != 0 ? 1u : 0u, issue);
-            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)k * bstep, idesc_k, (kb | k) != 0 ? 1u : 0u, issue);
+            if (PAIR) umma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)k * bstep, idesc_k, (kb != kb_lo || k != 0) ? 1u : 0u, issue);
+            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)k * bstep, idesc_k, (kb != kb_lo || k != 0) ? 1u : 0u, issue);
           }
           if (PAIR) umma_commit_pair(&empty[stage], issue); else umma_commit(&empty[stage], issue);   // smem stage free (in both CTAs) once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -971,8 +987,12 @@ int launch_gemm_tc(const TcPlan* pl, const GemmArgs& g, cudaStream_t s) {
   p.M = g.M;
   p.m_tiles = (g.M + TC_BM - 1) / TC_BM;
   p.gemm = 1; p.gemm_ntile_tap = g.Nper / pl->BN;
+  p.gemm_splits = g.splits > 0 ? g.splits : 1;
   p.n_tiles = g.ntaps * p.gemm_ntile_tap;
   p.kb_per_tap = (g.K + TC_BK - 1) / TC_BK;
+  p.gemm_kb_split = (p.kb_per_tap + p.gemm_splits - 1) / p.gemm_splits;
+  p.gemm_splits = (p.kb_per_tap + p.gemm_kb_split - 1) / p.gemm_kb_split;          // no empty split
+  YB_REQUIRE(p.gemm_splits == 1 || g.accumulate, YB_ERR_INVALID, "launch_gemm_tc: split-K needs accumulate (atomic) output");
   p.ntaps = 1; p.tap_shift[0] = 0;
   for (int i = 0; i < g.ntaps; ++i) p.gemm_shift[i] = g.shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
@@ -980,7 +1000,7 @@ int launch_gemm_tc(const TcPlan* pl, const GemmArgs& g, cudaStream_t s) {
   p.is_f16 = g.act_dt == DT_F16; p.alt_tiles = pl->alt_tiles;
   p.g.H = 1 << 20; p.g.W = 1 << 20;
   p.bias = nullptr; p.residual = nullptr; p.out = g.out;
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.gemm_splits;
   const int grid = total < pl->sms ? total : pl->sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = s;
@@ -1004,7 +1024,7 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
   p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a; p.alt_tiles = pl->alt_tiles;
-  p.gemm = 0; p.gemm_ntile_tap = 1; p.accumulate = 0;
+  p.gemm = 0; p.gemm_ntile_tap = 1; p.accumulate = 0; p.gemm_splits = 1; p.gemm_kb_split = 0;
   for (int i = 0; i < 16; ++i) p.gemm_shift[i] = 0;
   const int sms = pl->sms;
   const int total = p.m_tiles * p.n_tiles;

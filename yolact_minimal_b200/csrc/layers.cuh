@@ -71,6 +71,7 @@ bool tc_supported(const ConvArgs& a);
 struct GemmArgs {
   const void* a; const void* b; float* out;
   int act_dt, M, Nper, K, lda, ldb, ntaps, accumulate;
+  int splits;              // split-K pieces per output tile (needs accumulate = 1 and a zeroed / accumulating `out`); 0 / 1 = none
   long long Kb;            // addressable columns of b
   int shift[16];
 };

@@ -315,8 +315,16 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
       BWD_PUSH([=](cudaStream_t s) { return launch_transpose16(dy, Cg, dyT, dt, rows_y, Mrows, ldT, s); });
       GemmArgs g; memset(&g, 0, sizeof(g));
       g.a = dyT; g.b = src->data; g.out = c->dWp; g.act_dt = dt; g.M = c->Cout_pad; g.Nper = c->Cin_pad; g.K = (int)rows_y; g.lda = (int)ldT; g.ldb = src->C;
-      g.Kb = src->rows; g.accumulate = c->wgrad_set ? 1 : 0;
+      g.Kb = src->rows; g.accumulate = 1;                           // dWp is zero at the start of a backward pass (cleared by the unpack kernel)
       fill_taps_fwd(c, Wp, plane_rows, &g.ntaps, g.shift);
+      {  // split-K: a weight gradient has few output tiles and a long K (the pixels); cut K so that ~2 waves of CTAs are busy
+        const int bn = c->Cin_pad % 256 == 0 ? 256 : (c->Cin_pad % 128 == 0 ? 128 : 64);
+        const int tiles = ((c->Cout_pad + 127) / 128) * g.ntaps * (c->Cin_pad / bn);
+        const int kb_total = (int)((rows_y + 63) / 64);
+        int splits = (2 * 148 + tiles - 1) / tiles;
+        if (splits > kb_total / 4) splits = kb_total / 4;
+        g.splits = splits < 1 ? 1 : splits;
+      }
       YB_REQUIRE(c->Cin == c->Cin_pad, YB_ERR_UNSUPPORTED, "train: conv %s Cin=%d is not a multiple of 64", c->wname.c_str(), c->Cin);
       TcPlan* gp = nullptr;
       YB_PROPAGATE(tc_plan_create_gemm(g, &gp));
@@ -487,6 +495,7 @@ int build(yb_train* t) {
       BWD_PUSH([=](cudaStream_t s) { return launch_transpose16(dy, 64, dyT, dt, rows, 64, ldT, s); });
       GemmArgs g; memset(&g, 0, sizeof(g));
       g.a = dyT; g.b = s2dd; g.out = dW16; g.act_dt = dt; g.M = 64; g.Nper = 64; g.K = (int)rows; g.lda = (int)ldT; g.ldb = 64; g.Kb = rows; g.ntaps = 4;
+      g.accumulate = 1; g.splits = 74;                              // 4 output tiles, K = every pixel of the batch: split-K
       for (int dy_ = 0; dy_ < 4; ++dy_) g.shift[dy_] = (dy_ - 1) * Wp1 - 1;        // out [64][dy*64 + dx*16 + e]: the packed stem layout
       TcPlan* gp = nullptr;
       YB_PROPAGATE(tc_plan_create_gemm(g, &gp));

@@ -22,7 +22,7 @@ struct UnpackDesc {
 };
 int launch_pack_weights(const PackDesc* d_descs, int n, int dt, cudaStream_t s);
 int launch_pack_stem(const float* src, void* dst, int dt, cudaStream_t s);
-int launch_unpack_stem_grad(const float* g, float* dst, float scale, cudaStream_t s);
+int launch_unpack_stem_grad(float* g, float* dst, float scale, cudaStream_t s);
 int launch_unpack_wgrad(const UnpackDesc* d_descs, int n, cudaStream_t s);
 
 // ---- batch-statistics BatchNorm ----

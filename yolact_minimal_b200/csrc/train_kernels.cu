@@ -70,21 +70,24 @@ int launch_pack_stem(const float* src, void* dst, int dt, cudaStream_t s) {
 }
 
 // inverse for the gradient: packed fp32 [64][16 taps (dy,dx)][16] -> += / = grad [64][3][7][7]
-__global__ void k_unpack_stem_grad(const float* __restrict__ g, float* __restrict__ dst, float scale) {
+__global__ void k_unpack_stem_grad(float* __restrict__ g, float* __restrict__ dst, float scale) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= 64 * 147) return;
   const int q = i % 7, r = (i / 7) % 7, ci = (i / 49) % 3, co = i / 147;
   const int dy = (r + 1) >> 1, py = (r + 1) & 1, dx = (q + 1) >> 1, px = (q + 1) & 1;
-  dst[i] = scale * g[co * 256 + (dy * 4 + dx) * 16 + (py * 2 + px) * 3 + ci];
+  float* src = g + co * 256 + (dy * 4 + dx) * 16 + (py * 2 + px) * 3 + ci;
+  dst[i] = scale * *src;
+  *src = 0.f;
 }
 
-int launch_unpack_stem_grad(const float* g, float* dst, float scale, cudaStream_t s) {
+int launch_unpack_stem_grad(float* g, float* dst, float scale, cudaStream_t s) {
   k_unpack_stem_grad<<<ceil_div(64 * 147, 256), 256, 0, s>>>(g, dst, scale);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
 
-// packed weight gradients fp32 [Cout_total][taps][Cin_pad] -> parameter gradient [Cout][Cin][k][k] (batched)
+// packed weight gradients fp32 [Cout_total][taps][Cin_pad] -> parameter gradient [Cout][Cin][k][k] (batched); the packed buffer is
+// cleared behind the read: it is the atomically accumulated output of the split-K weight-gradient GEMMs
 __global__ void __launch_bounds__(256) k_unpack_wgrad(const UnpackDesc* __restrict__ descs) {
   const UnpackDesc d = descs[blockIdx.y];
   const int k2 = d.k * d.k;
@@ -93,7 +96,9 @@ __global__ void __launch_bounds__(256) k_unpack_wgrad(const UnpackDesc* __restri
     const int t = (int)(i % k2);
     const long long r = i / k2;
     const int ci = (int)(r % d.Cin), co = (int)(r / d.Cin);
-    d.dst[i] = d.scale * d.src[(long long)(d.row0 + co) * d.ld + (long long)t * d.Cin_pad + ci];
+    float* src = const_cast<float*>(d.src) + (long long)(d.row0 + co) * d.ld + (long long)t * d.Cin_pad + ci;
+    d.dst[i] = d.scale * *src;
+    *src = 0.f;                                                    // the split-K GEMMs of the next backward pass accumulate from zero
   }
 }
 
