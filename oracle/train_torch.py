@@ -92,7 +92,9 @@ def forward_train(net, img, taps=None, act=None, subst=None):
         box.append(_conv(pl.bbox_layer, f, q).permute(0, 2, 3, 1).reshape(B, -1, 4))
         coef.append(torch.tanh(_conv(pl.coef_layer[0], f, q)).permute(0, 2, 3, 1).reshape(B, -1, pl.coef_dim))
     seg = _conv(net.semantic_seg_conv, p3, q)
-    return torch.cat(cls, 1), torch.cat(box, 1), torch.cat(coef, 1), proto, seg
+    # the five network outputs (substitutable too: identical logits -> identical OHEM / target decisions in the losses)
+    return (tap('out.cls', torch.cat(cls, 1)), tap('out.box', torch.cat(box, 1)), tap('out.coef', torch.cat(coef, 1)), tap('out.proto', proto),
+            tap('out.seg', seg))
 
 
 # ----------------------------------------------------------------------------------------------------

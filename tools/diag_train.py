@@ -42,7 +42,9 @@ def engine(arch, S, B, precision, mode='fp32'):
     bn = sorted(o['bn'].items(), key=lambda kv: -kv[1])[:5]
     print('BN buffers worst abs err', bn)
 
-for fn, args in ((engine, ('res50', 128, 2, 'bf16', 'subst')), (engine, ('res50', 128, 2, 'fp16', 'subst')), (engine, ('res101', 96, 2, 'bf16', 'subst'))):
+import os
+ORDER = os.environ.get('ORDER', 'bf16,fp16').split(',')
+for fn, args in tuple((engine, ('res50', 128, 2, pr, 'subst')) for pr in ORDER):
     try:
         fn(*args)
     except Exception:

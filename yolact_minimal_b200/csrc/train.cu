@@ -324,6 +324,7 @@ int op_conv(yb_train* t, TT* x, ConvRec* c, int relu, bool out_dense, const std:
         int splits = (2 * 148 + tiles - 1) / tiles;
         if (splits > kb_total / 4) splits = kb_total / 4;
         g.splits = splits < 1 ? 1 : splits;
+        if (getenv("YOLACT_B200_TRAIN_NO_SPLITK")) g.splits = 1;              // tooling: A/B
       }
       YB_REQUIRE(c->Cin == c->Cin_pad, YB_ERR_UNSUPPORTED, "train: conv %s Cin=%d is not a multiple of 64", c->wname.c_str(), c->Cin);
       TcPlan* gp = nullptr;
@@ -983,6 +984,25 @@ extern "C" uint64_t yb_train_launches_per_step(const yb_train* t) { return t ? t
 
 extern "C" int yb_train_read(yb_train* t, const char* name, int grad, float* out, int64_t out_count, int* C, int* H, void* stream) {
   YB_REQUIRE(t && name, YB_ERR_INVALID, "yb_train_read: NULL argument");
+  {  // the network outputs the losses consume (dense fp32): "out.cls" [B,A,C], "out.box" [B,A,4], "out.coef" [B,A,K], "out.proto"
+     // [B,P,P,K], "out.seg" [B,Hs,Hs,ld] -- C / H report the last two extents
+    const std::string n(name);
+    const float* src = nullptr; int64_t cnt = 0; int c = 0, h = 0;
+    if (n == "out.cls") { src = t->cls; c = t->cfg.num_classes; h = t->A; cnt = (int64_t)t->B * t->A * c; }
+    else if (n == "out.box") { src = t->box; c = 4; h = t->A; cnt = (int64_t)t->B * t->A * 4; }
+    else if (n == "out.coef") { src = t->coef; c = t->cfg.coef_dim; h = t->A; cnt = (int64_t)t->B * t->A * c; }
+    else if (n == "out.proto") { src = t->proto; c = t->cfg.coef_dim; h = t->P; cnt = (int64_t)t->B * t->P * t->P * c; }
+    else if (n == "out.seg") { src = t->seg; c = t->ld_seg; h = t->Hs; cnt = (int64_t)t->B * t->Hs * t->Hs * c; }
+    if (src) {
+      YB_REQUIRE(!grad, YB_ERR_UNSUPPORTED, "yb_train_read: '%s' has no readable gradient", name);
+      if (C) *C = c;
+      if (H) *H = h;
+      if (!out) return YB_OK;
+      YB_REQUIRE(out_count >= cnt, YB_ERR_INVALID, "yb_train_read: output too small");
+      YB_CHECK_CUDA(cudaMemcpyAsync(out, src, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+      return YB_OK;
+    }
+  }
   auto it = t->by_name.find(name);
   YB_REQUIRE(it != t->by_name.end(), YB_ERR_INVALID, "yb_train_read: unknown tensor '%s'", name);
   const TT* x = it->second;

@@ -112,6 +112,19 @@ class TrainEngine:
                                             torch.cuda.current_stream().cuda_stream), 'yb_train_read')
         return out
 
+    def read_output(self, name):
+        """Debug / parity tap: a network output as the losses saw it -- 'cls' [B,A,C] raw logits, 'box' [B,A,4], 'coef' [B,A,K] (tanh),
+        'proto' [B,P,P,K], 'seg' [B,Hs,Hs,C-1] (NHWC)."""
+        C, H = ctypes.c_int(), ctypes.c_int()
+        key = ('out.' + name).encode()
+        _lib.check(self.L.yb_train_read(self.h, key, 0, None, 0, ctypes.byref(C), ctypes.byref(H), None), 'yb_train_read')
+        shape = (self.batch, H.value, C.value) if name in ('cls', 'box', 'coef') else (self.batch, H.value, H.value, C.value)
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.yb_train_read(self.h, key, 0, out.data_ptr(), out.numel(), ctypes.byref(C), ctypes.byref(H),
+                                            torch.cuda.current_stream().cuda_stream), 'yb_train_read')
+        return out
+
     def launches_per_step(self):
         return int(self.L.yb_train_launches_per_step(self.h))
 
