@@ -25,6 +25,7 @@ Rank 0 prints ONE JSON line:
   parity               the TIMED B=64 output itself: images 0/31/63 vs the fp32 oracle and bit-wise vs B=1 runs; N > 1: the
                        gathered records vs rank 0 re-running every rank's batch on one GPU, bit-for-bit.
   other_configs        BASELINE configs[1] (res50 bs32), configs[4] (swin_tiny bs32) and the 544 variants, N = 1.
+  mask_stage           after_nms for 100 detections at 480x640 (float32 / uint8 / bit-packed masks), mask IoU and RLE on the packed masks, N = 1.
   training             BASELINE configs[3]: res101 550x550 training step (native engine forward + backward + SGD), bs 2 per GPU, DDP over
                        NCCL at N > 1; at N = 1 beside the same step on torch autograd / cuDNN.
 `--impl reference` times the reference's CPU implementation of the path (the reference itself when staged, else the port).
@@ -272,6 +273,40 @@ def measure_config(arch, img_size, batch, precision, dev, steps, pk):
     torch.cuda.empty_cache()
     return {'workload': f'{arch}_coco {img_size}x{img_size} bs={batch}', 'value': v, 'unit': 'img/s', 'ms_per_step': ms, 'steps': steps,
             'tensor_frac_of_peak': v * gf * 1e9 / (pk['tf_sustained'] * 1e12) if gf else None}
+
+
+def mask_stage_leg(dev, pk, img_size=550, img_h=480, img_w=640, reps=20):
+    """after_nms (mask assembly: proto @ coef^T, sigmoid, crop, up-sampling to the image, threshold) for the 100 detections of one image,
+    in the reference's float32 mask format and in the byte / bit-packed formats, then the stage the reference's evaluation loop runs on
+    the masks (mask IoU against ground truth, COCO RLE).  Output-write bound: the roofline is the mask bytes written per image."""
+    import torch
+    from oracle import synth, postprocess_np as pp
+    from yolact_minimal_b200.utils.output_utils import after_nms
+    from yolact_minimal_b200.utils import mask_utils as mu
+    anchors = pp.make_anchors(img_size)
+    cls, box, coef = synth.head_outputs(5, anchors.shape[0], 81, 'realistic')
+    proto = synth.proto(5, (img_size + 3) // 4)
+    ids, scores, boxes, aidx = pp.nms(cls, box, anchors)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    args = (t(ids), t(scores), t(boxes), t(coef[aidx]), t(proto), img_h, img_w)
+    d = len(ids)
+    out = {'detections': d, 'image': f'{img_h}x{img_w}', 'proto': int(proto.shape[0])}
+    for name, dt, bpp in (('float32', torch.float32, 4.0), ('uint8', torch.uint8, 1.0), ('bits', 'bits', 0.125)):
+        for _ in range(3):
+            after_nms(*args, mask_dtype=dt)
+        ms = cuda_time(lambda i: after_nms(*args, mask_dtype=dt), reps)
+        wbytes = d * img_h * img_w * bpp
+        out[name] = {'ms_per_image': ms, 'mask_bytes_per_image': wbytes, 'write_gbs': wbytes / (ms * 1e-3) / 1e9, 'frac_of_hbm_peak': wbytes / (ms * 1e-3) / 1e9 / pk['hbm']}
+    bits = after_nms(*args, mask_dtype='bits')[3]
+    gt = bits[:20].contiguous()
+    for _ in range(3):
+        mu.mask_iou_bits(bits, gt)
+    out['mask_iou_100x20_ms'] = cuda_time(lambda i: mu.mask_iou_bits(bits, gt), reps)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        mu.encode_rle(bits, img_h, img_w)
+    out['rle_100_masks_ms_incl_host_string'] = (time.perf_counter() - t0) / 5 * 1e3
+    return out
 
 
 def training_leg(arch, img_size, per_gpu, steps, dev, rank, world):
@@ -625,6 +660,10 @@ def run_ours(args):
                     oc.append({'workload': f'{a_}_coco {s_}x{s_} bs={b_}', 'error': repr(e)[:200]})
             line['other_configs'] = oc
             line['training'] = training_leg(ARCH, IMG, 2, 50, dev, 0, 1)
+            try:
+                line['mask_stage'] = mask_stage_leg(dev, pk)
+            except Exception as e:
+                line['mask_stage'] = {'error': repr(e)[:300]}
         cores = host_cores()
         cpu_v, cpu_s, cpu_nms_us, kind = cpu_reference_sample(ARCH, IMG, 4, 6, cores)
         line['cpu_baseline'] = {'value': cpu_v, 'unit': 'img/s', 'cores': cores, 'kind': kind,

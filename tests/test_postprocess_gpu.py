@@ -132,6 +132,48 @@ def test_full_size_batch_properties(cuda):
         assert np.array_equal(r[k][perm], r3[k]), k                                      # images independent
 
 
+def test_sampled_cuts_cannot_change_the_result(cuda):
+    """The per-class candidate lists are filled from SAMPLED score cuts (k_sample_cuts reads the anchors floor(t*A/512));
+    exactness must not depend on the sample.  Adversarial images at the full head size: (0) the sampled anchors carry the high
+    scores of some classes and everything else is low -> the cut is too high, the list holds < top_k entries; (1) the sampled
+    anchors are low and > 2048 other anchors are high -> the list overflows; (2) > 2048 exactly tied scores at the top of a
+    class; (3) sampled anchors are not candidates at all (the image looks empty to the sample).  All four must take the exact
+    full-column path and equal the oracle bit for bit."""
+    S = 550
+    anchors = pp.make_anchors(S)
+    A = anchors.shape[0]
+    sampled = np.unique((np.arange(512, dtype=np.int64) * A) // 512)
+    others = np.setdiff1d(np.arange(A), sampled)
+    rng = np.random.default_rng(77)
+    imgs = []
+    for kind in range(4):
+        cls, box, coef = synth.head_outputs(300 + kind, A, 81, 'realistic')
+        cls = cls.copy()
+        hot = [3, 17, 40, 80]
+        if kind == 0:
+            for c in hot:
+                cls[:, c] = rng.uniform(0.06, 0.2, A).astype(np.float32)
+                cls[sampled, c] = rng.uniform(0.8, 0.99, sampled.size).astype(np.float32)
+        elif kind == 1:
+            for c in hot:
+                cls[:, c] = rng.uniform(0.06, 0.1, A).astype(np.float32)
+                hi = rng.choice(others, 6000, replace=False)
+                cls[hi, c] = rng.uniform(0.5, 0.99, hi.size).astype(np.float32)
+                cls[sampled, c] = 0.07
+        elif kind == 2:
+            for c in hot:
+                tied = rng.choice(A, 5000, replace=False)
+                cls[tied, c] = np.float32(0.75)
+        else:
+            cls[sampled, 1:] = 0.0
+            cls[sampled, 0] = 1.0
+        imgs.append((cls, box, coef))
+    cls = np.stack([i[0] for i in imgs]); box = np.stack([i[1] for i in imgs]); coef = np.stack([i[2] for i in imgs])
+    r = _run(cuda, cls, box, coef, anchors, _cfg(S=S))
+    for b in range(4):
+        _check_image(r, b, pp.nms(cls[b], box[b], anchors), coef[b])
+
+
 def test_hard_nms_vs_oracle_and_golden(cuda):
     from yolact_minimal_b200 import cython_nms
     g = load_golden('hard_nms.npz')
