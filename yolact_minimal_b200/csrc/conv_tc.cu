@@ -125,6 +125,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// bring one box of a tensor into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -772,6 +776,340 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 }
 
+
+// =================================================================================================================
+// Fused bottleneck tail + next head (layers.cuh BneckArgs): per 256-row pair tile
+//   for each 128-channel chunk c of the expanded width:   A(c):  accA[c&1]  = t2 * W3_c^T  (+ x_c through identity MMAs)
+//                                                         E1(c): x'_c = relu(accA + b3_c) -> 16 bit -> shared memory (128B-swizzled
+//                                                                k-blocks) -> TMA store to xo AND A operand of
+//                                                         B(c):  accB += x'_c * W1_c^T
+//   E2: t1 = relu(accB + b1) -> shared memory -> TMA store.
+// The MMA warp issues  A(0) A(1) B(0) A(2) B(1) ... A(7) B(6) B(7)  so the tensor pipe works on A(c+1) while the epilogue
+// warps turn chunk c around.  Shared memory per CTA: t2 tile resident (kbA x 16 KB), x' staging 2 x 32 KB, a 5-slot ring of
+// 16 KB (W3 k-block pairs, residual k-blocks, W1 k-blocks, streamed in exactly the order the MMA warp consumes them), identity
+// tile, biases.
+// TMEM: 2 x 128 columns accA + 256 columns accB = all 512.  Same pair conventions as k_conv_tc<., true>: loads land in
+// the issuing CTA's shared memory and are counted on the LEADER's barriers, commits are multicast to both CTAs, epilogue warps of
+// both CTAs arrive on the leader's barriers.
+// The residual x rides the ring as two more k-blocks per chunk and is added by the tensor core against an identity tile (the
+// res_kb form of k_conv_tc), so the arithmetic -- operand rounding points, k order, residual after the main k-blocks -- is that of
+// the two separate k_conv_tc launches and the fused result is BIT-IDENTICAL to the unfused one.  Reading the residual in the epilogue
+// instead (one 128-byte row segment per lane and chunk, straight from global memory, double-buffered in registers + L2 prefetch) frees
+// a third of the ring and 12 % of the MMA time but was 20-50 % slower: 8 lane-divergent 16-byte loads per thread and chunk through
+// an L1 that the 220 KB of shared memory leave 28 KB of (profiles/r2_bneck_experiments.txt).
+// =================================================================================================================
+constexpr int BK_SLOTS = 5;
+constexpr uint32_t BK_SLOT = 16384;
+
+struct BnParams {
+  long long M;
+  int m_tiles;              // pair tiles of 256 rows
+  int Cmid, Cexp, nchunks, kbA;
+  unsigned long long* trace;  // tooling (YOLACT_B200_BNECK_TRACE): cycle stamps, see k_bneck_tc
+  Geom g;
+  const float* b3;
+  const float* b1;
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW3,
+           const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmXo, const __grid_constant__ CUtensorMap tmT1,
+           const BnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* sT2 = smem;                                         // [kbA][128 rows x 128 B]
+  uint8_t* sX = sT2 + (size_t)p.kbA * TC_A_STAGE;              // [2 buffers][2 k-blocks][128 rows x 128 B]
+  uint8_t* sRing = sX + 4 * TC_A_STAGE;                        // [BK_SLOTS][16 KB]
+  uint8_t* sEye = sRing + (size_t)BK_SLOTS * BK_SLOT;          // [32 rows][128 B]: this CTA's half of the 64 x 64 identity
+  float* sBias = reinterpret_cast<float*>(sEye + 4096);        // [Cexp] b3 then [Cmid] b1: read by every epilogue warp, every chunk
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBias + p.Cexp + p.Cmid);   // [8]
+  uint64_t* empty = full + 8;                                  // [8]
+  uint64_t* t2_full = empty + 8;
+  uint64_t* t2_empty = t2_full + 1;
+  uint64_t* accA_full = t2_empty + 1;                          // [2]
+  uint64_t* accA_empty = accA_full + 2;                        // [2]
+  uint64_t* accB_full = accA_empty + 2;
+  uint64_t* accB_empty = accB_full + 1;
+  uint64_t* xs_full = accB_empty + 1;                          // [2]  x' chunk staged by all 16 epilogue warps of the pair
+  uint64_t* xs_empty = xs_full + 2;                            // [2]  B(c) finished reading the staging buffer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xs_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmT2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(t2_full, 1); mbar_init(t2_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&accA_full[i], 1); mbar_init(&accA_empty[i], 16);
+      mbar_init(&xs_full[i], 16); mbar_init(&xs_empty[i], 1);
+    }
+    mbar_init(accB_full, 1); mbar_init(accB_empty, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    // identity rows 32*rank .. 32*rank+31 (see k_conv_tc): row n has 1.0 at element 32*rank + n, chunk (k/8) ^ (n & 7)
+    const int t = (int)threadIdx.x - 64, n = t >> 2;
+    if (n < 32) {
+      const int kone = n + 32 * (int)rank;
+      const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = (t & 3) * 2 + q;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c == (kone >> 3)) {
+          const int e = kone & 7;
+          const uint32_t w = (e & 1) ? (one << 16) : one;
+          if ((e >> 1) == 0) v.x = w; else if ((e >> 1) == 1) v.y = w; else if ((e >> 1) == 2) v.z = w; else v.w = w;
+        }
+        *reinterpret_cast<uint4*>(sEye + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+      }
+    }
+    fence_async_smem();
+    for (int i = t; i < p.Cexp + p.Cmid; i += TC_THREADS - 64) sBias[i] = i < p.Cexp ? __ldg(p.b3 + i) : __ldg(p.b1 + i - p.Cexp);   // constants: before griddep_wait
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  griddep_launch_dependents();
+
+  const int unit = (int)(blockIdx.x >> 1), units = (int)(gridDim.x >> 1);
+  // tooling: cycle stamps of the leader CTA of pair 0 (YOLACT_B200_BNECK_TRACE), 8 events x 64 chunks
+  unsigned long long* const trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+  auto stamp = [&](int ev, uint32_t qq) { if (trace && qq < 64u) trace[ev * 64 + qq] = (unsigned long long)clock64(); };
+  const int nch = p.nchunks, kbA = p.kbA;
+  const uint32_t w1_bytes = (uint32_t)(p.Cmid / 2) * 128u;            // one W1 k-block of this CTA: Cmid/2 rows x 128 B
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs; bytes counted on the leader's barriers) =================
+    if (lane == 0) {
+      griddep_wait();
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t t2_full_addr = map_to_rank(smem_u32(t2_full), 0);
+      auto load_a = [&](int c, int row0) {                              // operands of A(c): W3 chunk (two k-blocks per slot), residual chunk
+        for (int s = 0; s < kbA / 2; ++s) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t fa = map_to_rank(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * BK_SLOT);
+          for (int j = 0; j < 2; ++j)
+            tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT + (size_t)j * 8192, &tmW3, (2 * s + j) * TC_BK, c * 128 + (int)rank * 64, fa);
+          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+        }
+        for (int j = 0; j < 2; ++j) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t fa = map_to_rank(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * BK_SLOT);
+          tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT, &tmX, c * 128 + j * TC_BK, row0, fa);
+          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+        }
+      };
+      auto load_b = [&](int c) {                                        // B operand of B(c): W1[:, c*128 .. +127], two k-blocks
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t fa = map_to_rank(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * w1_bytes);
+          tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT, &tmW1, c * 128 + kb * TC_BK, (int)rank * (p.Cmid / 2), fa);
+          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+        }
+      };
+      for (int i = 0; unit + i * units < p.m_tiles; ++i) {
+        const int row0 = (2 * (unit + i * units) + (int)rank) * TC_BM;
+        mbar_wait(t2_empty, (uint32_t)(i & 1) ^ 1u);                    // A(last) of the previous tile has read the t2 tile
+        if (rank == 0) mbar_expect_tx(t2_full, 2u * (uint32_t)kbA * TC_A_STAGE);
+        for (int kb = 0; kb < kbA; ++kb) tma_load_2d_pair(sT2 + (size_t)kb * TC_A_STAGE, &tmT2, kb * TC_BK, row0, t2_full_addr);
+        for (int c = 0; c < nch; ++c) {
+          load_a(c, row0);
+          if (c >= 1) load_b(c - 1);
+        }
+        load_b(nch - 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA) =================
+    if (rank == 0) {
+      const uint32_t issue = elect_one();
+      const uint32_t fmt = F16 ? 0u : 1u;
+      const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      const uint32_t idescA = idesc0 | ((uint32_t)(128 >> 3) << 17);
+      const uint32_t idescE = idesc0 | ((uint32_t)(64 >> 3) << 17);
+      const uint32_t idescB = idesc0 | ((uint32_t)(p.Cmid >> 3) << 17);
+      const uint32_t dB = tmem_base + 256u;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t q = 0;                                                   // chunk sequence number over all tiles of this pair
+      auto issue_b = [&](int c, uint32_t qq, int i) {
+        const int buf = (int)(qq & 1u);
+        if (lane == 0) stamp(2, qq);
+        mbar_wait(&xs_full[buf], (qq >> 1) & 1u);                       // x' chunk staged in both CTAs (generic writes + proxy fence)
+        if (lane == 0) stamp(3, qq);
+        if (c == 0) { mbar_wait(accB_empty, (uint32_t)(i & 1) ^ 1u); }  // E2 of the previous tile has drained accB
+        tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc(smem_u32(sX + (size_t)buf * 2 * TC_A_STAGE + (size_t)kb * TC_A_STAGE));
+          const uint64_t db = umma_desc(smem_u32(sRing + (size_t)stage * BK_SLOT));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) umma_pair(dB, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idescB, (c | kb | k) != 0 ? 1u : 0u, issue);
+          umma_commit_pair(&empty[stage], issue);
+          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&xs_empty[buf], issue);
+      };
+      for (int i = 0; unit + i * units < p.m_tiles; ++i) {
+        mbar_wait(t2_full, (uint32_t)(i & 1));
+        tc_fence_after();
+        for (int c = 0; c < nch; ++c, ++q) {
+          const int a = (int)(q & 1u);
+          if (lane == 0) stamp(0, q);
+          mbar_wait(&accA_empty[a], ((q >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t dA = tmem_base + (uint32_t)(a * 128);
+          for (int s = 0; s < kbA / 2; ++s) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int kb = 2 * s + j;
+              const uint64_t da = umma_desc(smem_u32(sT2 + (size_t)kb * TC_A_STAGE));
+              const uint64_t db = umma_desc(smem_u32(sRing + (size_t)stage * BK_SLOT + (size_t)j * 8192));
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) umma_pair(dA, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idescA, (kb | k) != 0 ? 1u : 0u, issue);
+            }
+            umma_commit_pair(&empty[stage], issue);
+            if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+          }
+          for (int j = 0; j < 2; ++j) {                                 // accA[:, 64j .. 64j+63] += x_j * I
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc(smem_u32(sRing + (size_t)stage * BK_SLOT));
+            const uint64_t db = umma_desc(smem_u32(sEye));
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_pair(dA + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idescE, 1u, issue);
+            umma_commit_pair(&empty[stage], issue);
+            if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(&accA_full[a], issue);
+          if (lane == 0) stamp(1, q);
+          if (c == nch - 1) umma_commit_pair(t2_empty, issue);
+          if (c >= 1) issue_b(c - 1, q - 1, i);
+        }
+        issue_b(nch - 1, q - 1, i);
+        umma_commit_pair(accB_full, issue);
+      }
+    }
+  } else {
+    // ================= epilogue: warp (grp, quad) owns rows quad*32.. of the 64-column half `grp` of every chunk =================
+    const int wslot = warp - 2, grp = wslot >> 2, quad = warp & 3;
+    const bool elected = lane == 0;
+    griddep_wait();
+    uint8_t* const slab0 = sX + (size_t)grp * TC_A_STAGE + (size_t)quad * 4096;      // this warp's 32 x 128 B slab in staging buffer 0; buffer 1 is 32 KB on
+    const uint32_t accA_empty_l = map_to_rank(smem_u32(&accA_empty[0]), 0), xs_full_l = map_to_rank(smem_u32(&xs_full[0]), 0);
+    const uint32_t accB_empty_l = map_to_rank(smem_u32(accB_empty), 0);
+    const uint32_t sw = (uint32_t)(lane & 7);                          // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t q = 0;
+    // one 32-row x 32-column piece: TMEM -> +bias -> ReLU -> 16-bit -> 4 swizzled 16-byte stores into the warp's slab
+    auto piece = [&](const uint32_t* r, const float* bias, bool zero_row, uint8_t* row, int h) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + i);
+        pk[i / 2] = pack2_sat<F16, true>(__uint_as_float(r[i]) + b.x, __uint_as_float(r[i + 1]) + b.y);
+        pk[i / 2 + 1] = pack2_sat<F16, true>(__uint_as_float(r[i + 2]) + b.z, __uint_as_float(r[i + 3]) + b.w);
+      }
+      if (zero_row) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        *reinterpret_cast<uint4*>(row + ((((uint32_t)(h * 4 + jj)) ^ sw) << 4)) = make_uint4(pk[jj * 4], pk[jj * 4 + 1], pk[jj * 4 + 2], pk[jj * 4 + 3]);
+    };
+    for (int i = 0; unit + i * units < p.m_tiles; ++i) {
+      const int row0 = (2 * (unit + i * units) + (int)rank) * TC_BM + quad * 32;
+      const long long m = (long long)row0 + lane;
+      bool zero_row = m >= p.M;
+      if (!zero_row) {
+        const int pos = (int)(m % p.g.plane());
+        const int y = pos / p.g.Wp(), x = pos - y * p.g.Wp();
+        zero_row = y == 0 || y == p.g.H + 1 || x == 0 || x == p.g.W + 1;
+      }
+      for (int c = 0; c < nch; ++c, ++q) {
+        const int a = (int)(q & 1u);                                    // accumulator buffer == staging buffer of chunk q
+        mbar_wait(&accA_full[a], (q >> 1) & 1u);
+        if (warp == 2 && lane == 0) stamp(4, q);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t t_addr = t_lane + (uint32_t)(a * 128 + grp * 64);
+        tmem_ld32(t_addr, r0);
+        tmem_ld32(t_addr + 32, r1);
+        mbar_wait(&xs_empty[a], ((q >> 1) & 1u) ^ 1u);                  // B(q-2) has read this staging buffer
+        if (elected) bulk_wait_read<1>();                               // ... and so has this warp's TMA store of chunk q-2
+        __syncwarp();
+        tmem_ld_wait();
+        if (warp == 2 && lane == 0) stamp(5, q);
+        tc_fence_before();
+        uint8_t* const slab = slab0 + (size_t)a * 2 * TC_A_STAGE;
+        uint8_t* row = slab + lane * 128;
+        const float* bias = sBias + c * 128 + grp * 64;
+        piece(r0, bias, zero_row, row, 0);
+        piece(r1, bias + 32, zero_row, row, 1);
+        fence_async_smem();
+        __syncwarp();
+        if (elected) {
+          mbar_arrive_cluster(accA_empty_l + (uint32_t)a * 8u);
+          mbar_arrive_cluster(xs_full_l + (uint32_t)a * 8u);
+          tma_store_2d(&tmXo, slab, c * 128 + grp * 64, row0);
+          bulk_commit();
+          if (warp == 2) stamp(6, q);
+        }
+      }
+      // ---- E2: t1 = relu(accB + b1), this warp's Cmid/2 columns in 64-column slabs (staging buffers 0 and 1 in turn) ----
+      mbar_wait(accB_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      for (int j = 0; j < p.Cmid / 128; ++j) {
+        uint32_t r0[32], r1[32];
+        const int col = grp * (p.Cmid / 2) + j * 64;
+        tmem_ld32(t_lane + 256u + (uint32_t)col, r0);
+        tmem_ld32(t_lane + 256u + (uint32_t)col + 32u, r1);
+        if (elected) bulk_wait_read<1>();
+        __syncwarp();
+        tmem_ld_wait();
+        uint8_t* const slab = slab0 + (size_t)(j & 1) * 2 * TC_A_STAGE;
+        uint8_t* row = slab + lane * 128;
+        piece(r0, sBias + p.Cexp + col, zero_row, row, 0);
+        piece(r1, sBias + p.Cexp + col + 32, zero_row, row, 1);
+        fence_async_smem();
+        __syncwarp();
+        if (elected) {
+          tma_store_2d(&tmT1, slab, col, row0);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (elected) mbar_arrive_cluster(accB_empty_l);
+    }
+    if (elected) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -940,6 +1278,8 @@ static int tc_device_setup(int* sms) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_bneck_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_bneck_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     done[dev] = true;
   }
   YB_CHECK_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1062,4 +1402,83 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   return YB_OK;
 }
 
+// ---- fused bottleneck tail (k_bneck_tc) ------------------------------------------------------------------------------
+struct BnPlan {
+  CUtensorMap tmT2, tmX, tmW3, tmW1, tmXo, tmT1;
+  int sms, Cmid, Cexp;
+  size_t smem_bytes;
+};
+
+bool bneck_supported(int act_dt, int Cmid, int Cexp) {
+  // Cmid = 256: accB fills the 256 TMEM columns next to the two 128-column accA buffers, and E2's two 64-column slabs per warp
+  // keep the staging buffers alternating (the bulk-group accounting of the epilogue relies on it)
+  return (act_dt == DT_F16 || act_dt == DT_BF16) && Cmid == 256 && Cexp % 256 == 0 && Cexp >= 256 && !getenv("YOLACT_B200_NO_FUSE");
+}
+
+int bneck_plan_create(const BneckArgs& a, int max_batch, BnPlan** out) {
+  YB_REQUIRE(bneck_supported(a.act_dt, a.Cmid, a.Cexp), YB_ERR_UNSUPPORTED, "bneck_plan_create: unsupported Cmid=%d Cexp=%d", a.Cmid, a.Cexp);
+  BnPlan* pl = new BnPlan();
+  pl->Cmid = a.Cmid; pl->Cexp = a.Cexp;
+  const bool f16 = a.act_dt == DT_F16;
+  const uint64_t rows = (uint64_t)max_batch * a.g.plane();
+  int s = make_map(&pl->tmT2, a.t2, (uint64_t)a.Cmid, rows, TC_BM, f16);
+  if (s == YB_OK) s = make_map(&pl->tmX, a.x, (uint64_t)a.Cexp, rows, TC_BM, f16);
+  if (s == YB_OK) s = make_map(&pl->tmW3, a.w3, (uint64_t)a.Cmid, (uint64_t)a.Cexp, 64, f16);
+  if (s == YB_OK) s = make_map(&pl->tmW1, a.w1, (uint64_t)a.Cexp, (uint64_t)a.Cmid, (uint32_t)(a.Cmid / 2), f16);
+  if (s == YB_OK) s = make_map(&pl->tmXo, a.xo, (uint64_t)a.Cexp, rows, 32, f16);
+  if (s == YB_OK) s = make_map(&pl->tmT1, a.t1, (uint64_t)a.Cmid, rows, 32, f16);
+  if (s == YB_OK) s = tc_device_setup(&pl->sms);
+  if (s != YB_OK) { delete pl; return s; }
+  pl->smem_bytes = 1024 + (size_t)(a.Cmid / 64) * TC_A_STAGE + 4 * TC_A_STAGE + (size_t)BK_SLOTS * BK_SLOT + 4096 + (size_t)(a.Cexp + a.Cmid) * 4 + 1024;
+  YB_REQUIRE(pl->smem_bytes <= 227 * 1024, YB_ERR_UNSUPPORTED, "bneck_plan_create: %zu bytes of shared memory", pl->smem_bytes);
+  *out = pl;
+  return YB_OK;
+}
+
+void bneck_plan_destroy(BnPlan* p) { delete p; }
+
+static unsigned long long* g_bneck_trace = nullptr;     // tooling: stamps of the most recent launch (yb_debug_bneck_trace)
+
+int launch_bneck_tc(const BnPlan* pl, const BneckArgs& a, cudaStream_t s) {
+  BnParams p;
+  p.M = (long long)a.B * a.g.plane();
+  p.m_tiles = (int)((p.M + 2 * TC_BM - 1) / (2 * TC_BM));
+  p.Cmid = a.Cmid; p.Cexp = a.Cexp; p.nchunks = a.Cexp / 128; p.kbA = a.Cmid / 64;
+  p.g = a.g; p.b3 = a.b3; p.b1 = a.b1;
+  p.trace = nullptr;
+  if (getenv("YOLACT_B200_BNECK_TRACE")) {
+    if (!g_bneck_trace) { YB_CHECK_CUDA(cudaMalloc(&g_bneck_trace, 8 * 64 * 8)); }
+    YB_CHECK_CUDA(cudaMemsetAsync(g_bneck_trace, 0, 8 * 64 * 8, s));
+    p.trace = g_bneck_trace;
+  }
+  const int max_units = pl->sms / 2;
+  const int units = p.m_tiles < max_units ? p.m_tiles : max_units;
+  static const bool pdl = getenv("YOLACT_B200_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * units)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+  ++na;
+  cfg.attrs = attr; cfg.numAttrs = na;
+  const cudaError_t le = a.act_dt == DT_F16
+      ? cudaLaunchKernelEx(&cfg, k_bneck_tc<true>, pl->tmT2, pl->tmX, pl->tmW3, pl->tmW1, pl->tmXo, pl->tmT1, p)
+      : cudaLaunchKernelEx(&cfg, k_bneck_tc<false>, pl->tmT2, pl->tmX, pl->tmW3, pl->tmW1, pl->tmXo, pl->tmT1, p);
+  YB_CHECK_CUDA(le);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
 }  // namespace yb
+
+// tooling (tools/bneck_trace.py): copy out the cycle stamps of the most recent k_bneck_tc launch made with YOLACT_B200_BNECK_TRACE set
+extern "C" __attribute__((visibility("default"))) int yb_debug_bneck_trace(unsigned long long* out, int count) {
+  if (!yb::g_bneck_trace || count > 8 * 64) return -1;
+  return cudaMemcpy(out, yb::g_bneck_trace, (size_t)count * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}

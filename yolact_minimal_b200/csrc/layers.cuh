@@ -78,6 +78,23 @@ struct GemmArgs {
 int tc_plan_create_gemm(const GemmArgs& g, TcPlan** out);
 int launch_gemm_tc(const TcPlan* p, const GemmArgs& g, cudaStream_t s);
 
+// Fused tail of one ResNet bottleneck and head of the next (modules/resnet.py:20-40, stride-1 blocks of one stage):
+//   xo = relu(W3 * t2 + b3 + x)            1x1 Cmid -> Cexp, residual x, written out (the next block's residual / the stage output)
+//   t1 = relu(W1 * xo + b1)                1x1 Cexp -> Cmid of the NEXT block, fed from shared memory: xo is never re-read from HBM
+// All four tensors are haloed NHWC with the same geometry; weights are the packed K-major matrices of the two convolutions.
+struct BneckArgs {
+  const void* t2; const void* x; const void* w3; const void* w1;
+  const float* b3; const float* b1;
+  void* xo; void* t1;
+  int act_dt, B, Cmid, Cexp;
+  Geom g;
+};
+struct BnPlan;
+bool bneck_supported(int act_dt, int Cmid, int Cexp);
+int bneck_plan_create(const BneckArgs& a_maxbatch, int max_batch, BnPlan** out);
+void bneck_plan_destroy(BnPlan* p);
+int launch_bneck_tc(const BnPlan* p, const BneckArgs& a, cudaStream_t s);
+
 int launch_stem(const float* img_nchw, const float* w /*[7][7][3][64]*/, const float* bias, void* out, int out_dt,
                 int B, int S, int H1, cudaStream_t s);
 int launch_stem_s2d(const float* img_nchw, void* out /*[B][(H1+2)^2][16 | 64]*/, int dt, int wide, int B, int S, int H1, cudaStream_t s);

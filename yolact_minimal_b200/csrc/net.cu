@@ -35,7 +35,7 @@ struct ActBuf {
   int pad_rows = 0;            // extra pixel rows allocated behind the last image (stem space-to-depth image, see OP_STEM)
 };
 
-enum OpKind { OP_STEM, OP_POOL, OP_SPLIT, OP_CONV, OP_UPADD, OP_UP2X, OP_HEADFIN, OP_PATCH_EMBED, OP_LN, OP_ATTN, OP_MERGE_LN };
+enum OpKind { OP_STEM, OP_POOL, OP_SPLIT, OP_CONV, OP_UPADD, OP_UP2X, OP_HEADFIN, OP_PATCH_EMBED, OP_LN, OP_ATTN, OP_MERGE_LN, OP_BNECK };
 enum ExtOut { EXT_NONE = 0, EXT_PROTO = 1 };
 
 struct ConvW {                 // one packed convolution
@@ -56,6 +56,9 @@ struct Op {
   std::string p0, p1, p2;      // Swin ops: parameter names (LayerNorm weight/bias; attention: qkv bias, rel-pos table)
   int heads = 0, shift = 0;    // attention
   TcPlan* tc = nullptr;
+  // OP_BNECK (fuse_bottlenecks): conv3 (`conv`, in, res -> out) of one bottleneck chained into conv1 (`conv2`, out -> out2) of the next
+  int conv2 = -1, out2 = -1;
+  BnPlan* bn = nullptr;
 };
 
 }  // namespace
@@ -66,7 +69,8 @@ struct yb_net {
   std::map<std::string, int> pidx;
   std::vector<ActBuf> acts;
   std::vector<ConvW> convs;
-  std::vector<Op> ops;
+  std::vector<Op> ops;                      // the program that runs (finalize: ops_base with the fusable pairs merged)
+  std::vector<Op> ops_base;                 // one op per reference layer, as build_program wrote it
   std::map<std::string, int> taps;          // debug taps: name -> act
   std::vector<void*> slots;
   std::vector<size_t> slot_bytes;
@@ -341,13 +345,52 @@ void build_program(yb_net* net) {
   }
 }
 
+// 16-bit modes: merge [1x1 Cmid->Cexp + residual + ReLU] followed by [1x1 Cexp->Cmid + ReLU] (conv3 of a bottleneck and conv1 of the
+// next, modules/resnet.py:20-40) into one OP_BNECK where k_bneck_tc supports the widths (layer3: 256 / 1024)
+void fuse_bottlenecks(yb_net* net) {
+  if (net->act_dt == DT_F32 || getenv("YOLACT_B200_NO_TC")) return;
+  std::vector<Op> merged;
+  for (size_t i = 0; i < net->ops.size(); ++i) {
+    const Op& a = net->ops[i];
+    if (i + 1 < net->ops.size() && a.kind == OP_CONV && net->ops[i + 1].kind == OP_CONV) {
+      const Op& b = net->ops[i + 1];
+      const ConvW& ca = net->convs[a.conv];
+      const ConvW& cb = net->convs[b.conv];
+      const bool ok = ca.k == 1 && cb.k == 1 && a.stride == 1 && b.stride == 1 && a.res >= 0 && b.res < 0 && a.relu == 1 && b.relu == 1 &&
+                      a.out_mode == 0 && b.out_mode == 0 && a.ext == EXT_NONE && b.ext == EXT_NONE && b.in == a.out && ca.cat.empty() &&
+                      cb.cat.empty() && ca.Cout == cb.Cin && cb.Cout == ca.Cin && ca.Cin == ca.Cin_pad && cb.Cin == cb.Cin_pad &&
+                      ca.Cout == ca.Cout_pad && cb.Cout == cb.Cout_pad && bneck_supported(net->act_dt, ca.Cin, ca.Cout);
+      if (ok) {
+        Op f = a;
+        f.kind = OP_BNECK; f.conv2 = b.conv; f.out2 = b.out;
+        merged.push_back(f);
+        ++i;
+        continue;
+      }
+    }
+    merged.push_back(a);
+  }
+  net->ops.swap(merged);
+}
+
+void bneck_args(const yb_net* net, const Op& o, int B, BneckArgs* a) {
+  const ConvW& c3 = net->convs[o.conv];
+  const ConvW& c1 = net->convs[o.conv2];
+  memset(a, 0, sizeof(*a));
+  a->t2 = net->slots[net->acts[o.in].slot]; a->x = net->slots[net->acts[o.res].slot];
+  a->xo = net->slots[net->acts[o.out].slot]; a->t1 = net->slots[net->acts[o.out2].slot];
+  a->w3 = c3.d_w; a->b3 = c3.d_b; a->w1 = c1.d_w; a->b1 = c1.d_b;
+  a->act_dt = net->act_dt; a->B = B; a->Cmid = c3.Cin; a->Cexp = c3.Cout;
+  a->g.H = net->acts[o.in].H; a->g.W = a->g.H;
+}
+
 // liveness + slot assignment
 void plan_memory(yb_net* net) {
   auto& acts = net->acts;
   for (auto& a : acts) { a.first = 1 << 30; a.last = -1; }
   for (int i = 0; i < (int)net->ops.size(); ++i) {
     const Op& o = net->ops[i];
-    for (int t : {o.in, o.out, o.res, o.aux}) {
+    for (int t : {o.in, o.out, o.res, o.aux, o.out2}) {
       if (t < 0) continue;
       acts[t].first = acts[t].first < i ? acts[t].first : i;
       acts[t].last = acts[t].last > i ? acts[t].last : i;
@@ -492,6 +535,7 @@ extern "C" int yb_net_create(const yb_net_config* cfg, yb_net** out) {
   yb_net* net = new yb_net();
   net->cfg = *cfg;
   build_program(net);
+  net->ops_base = net->ops;
   *out = net;
   return YB_OK;
 }
@@ -500,7 +544,7 @@ extern "C" void yb_net_destroy(yb_net* net) {
   if (!net) return;
   for (void* p : net->slots) cudaFree(p);
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); }
-  for (auto& o : net->ops) tc_plan_destroy(o.tc);
+  for (auto& o : net->ops) { tc_plan_destroy(o.tc); bneck_plan_destroy(o.bn); }
   for (auto& kv : net->d_vec) cudaFree(kv.second);
   cudaFree(net->d_pe_w);
   for (void* p : {(void*)net->d_anchors, (void*)net->d_stem_w, (void*)net->d_stem_b, net->d_stem_w16, (void*)net->d_stem_b16, (void*)net->d_img, (void*)net->d_cls,
@@ -549,12 +593,14 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   for (void* p : net->slots) cudaFree(p);
   net->slots.clear();
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); c.d_w = nullptr; c.d_b = nullptr; }
-  for (auto& o : net->ops) { tc_plan_destroy(o.tc); o.tc = nullptr; }
+  for (auto& o : net->ops) { tc_plan_destroy(o.tc); bneck_plan_destroy(o.bn); }
+  net->ops = net->ops_base;
   cudaFree(net->d_anchors); cudaFree(net->d_stem_w); cudaFree(net->d_stem_b); cudaFree(net->d_stem_w16); cudaFree(net->d_stem_b16);
   net->d_anchors = net->d_stem_w = net->d_stem_b = net->d_stem_b16 = nullptr; net->d_stem_w16 = nullptr;
 
   net->max_batch = max_batch; net->precision = precision;
   net->act_dt = precision == YB_PREC_BF16 ? DT_BF16 : (precision == YB_PREC_FP16 ? DT_F16 : DT_F32);
+  fuse_bottlenecks(net);
   plan_memory(net);
   net->slots.resize(net->slot_bytes.size(), nullptr);
   for (size_t s = 0; s < net->slot_bytes.size(); ++s) {
@@ -620,6 +666,12 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
       YB_PROPAGATE(tc_plan_create(a, max_batch, &so.tc));
     }
     for (auto& o : net->ops) {
+      if (o.kind == OP_BNECK) {
+        BneckArgs b;
+        bneck_args(net, o, max_batch, &b);
+        YB_PROPAGATE(bneck_plan_create(b, max_batch, &o.bn));
+        continue;
+      }
       if (o.kind != OP_CONV) continue;
       ConvArgs a;
       static float dummy;
@@ -698,6 +750,12 @@ extern "C" int yb_net_forward(yb_net* net, const float* img, int batch, float* c
         else YB_PROPAGATE(launch_conv_simt(a, s));
         break;
       }
+      case OP_BNECK: {
+        BneckArgs b;
+        bneck_args(net, o, batch, &b);
+        YB_PROPAGATE(launch_bneck_tc(o.bn, b, s));
+        break;
+      }
       case OP_UPADD:
         YB_PROPAGATE(launch_upsample_add(act_ptr(net, o.in), act_ptr(net, o.out), net->act_dt, batch, 256, net->acts[o.in].H,
                                          net->acts[o.out].H, s));
@@ -743,8 +801,8 @@ extern "C" int yb_net_set_profiling(yb_net* net, int enable) {
 extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, int* num_entries) {
   YB_REQUIRE(net && out && num_entries, YB_ERR_INVALID, "yb_net_profile: NULL argument");
   static const char* kNames[] = {"conv_tc", "conv_simt", "stem", "maxpool", "phase_split", "upsample_add", "upsample2x", "head_finalize",
-                                 "patch_embed", "layernorm", "window_attention", "patch_merge_ln"};
-  const int NK = 12;
+                                 "patch_embed", "layernorm", "window_attention", "patch_merge_ln", "bneck_tc"};
+  const int NK = 13;
   YB_REQUIRE(max_entries >= NK, YB_ERR_INVALID, "yb_net_profile: need room for %d entries", NK);
   for (int i = 0; i < NK; ++i) { memset(&out[i], 0, sizeof(out[i])); strncpy(out[i].name, kNames[i], sizeof(out[i].name) - 1); }
   const size_t esz = dtype_size(net->act_dt);
@@ -770,6 +828,14 @@ extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, 
                   px * c.Cout * (o.out_mode == 1 ? 4 : esz) + (o.res >= 0 ? px * c.Cout * esz : 0);
           break;
         }
+        case OP_BNECK: {                                               // both convolutions; x' written once and never re-read
+          const ConvW& c3 = net->convs[o.conv];
+          const double Ho = net->acts[o.in].H, px = B * Ho * Ho;
+          k = 12;
+          flops = 4.0 * px * c3.Cout * c3.Cin;
+          bytes = px * esz * (2.0 * c3.Cin + 2.0 * c3.Cout) + 2.0 * c3.Cout * c3.Cin * esz;
+          break;
+        }
         case OP_STEM: k = 2; flops = 2.0 * B * net->H1 * net->H1 * 64 * 147; bytes = B * 3.0 * net->cfg.img_size * net->cfg.img_size * 4 + B * net->H1 * net->H1 * 64.0 * esz; break;
         case OP_POOL: k = 3; bytes = B * 64.0 * esz * ((double)net->H1 * net->H1 + (double)net->H2 * net->H2); break;
         case OP_SPLIT: { k = 4; const ActBuf& a = net->acts[o.out]; bytes = 2.0 * B * a.H * a.H * a.planes * a.C * esz; break; }
@@ -783,9 +849,9 @@ extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, 
         case OP_MERGE_LN: { k = 11; const ActBuf& a = net->acts[o.out]; bytes = 2.0 * B * a.H * a.H * a.C * esz; break; }
       }
       if (dump) {
-        const ConvW* c = o.kind == OP_CONV ? &net->convs[o.conv] : nullptr;
+        const ConvW* c = (o.kind == OP_CONV || o.kind == OP_BNECK) ? &net->convs[o.conv] : nullptr;
         fprintf(dump, "%zu,%zu,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.4f\n", f, i, (int)o.kind, o.tc ? 1 : 0, c ? c->Cin : 0, c ? c->Cout_pad : 0,
-                c ? c->k : 0, o.stride, o.kind == OP_CONV ? net->acts[o.in].H : 0, (int)B, ms, flops * 1e-9);
+                c ? c->k : 0, o.stride, c ? net->acts[o.in].H : 0, (int)B, ms, flops * 1e-9);
       }
       out[k].launches += (o.kind == OP_STEM ? 2 : 1);
       out[k].ms += ms; out[k].flops += flops; out[k].bytes += bytes;
