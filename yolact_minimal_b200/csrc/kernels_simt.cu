@@ -3,6 +3,7 @@
 // split for stride-2 convs, FPN upsample+add, protonet upsample, head softmax/tanh scatter).
 // All activations use the haloed NHWC layout described in layers.cuh.
 #include "layers.cuh"
+#include <mutex>
 #include "vecio.cuh"
 #include <math.h>
 #include <algorithm>
@@ -251,6 +252,30 @@ int launch_stem(const float* img, const float* w, const float* bias, void* out, 
 // ------------------------------------------------------------------------------------------------
 // Elementwise kernels use a (x*channel-vectors, y, image) launch geometry: no 64-bit index arithmetic
 // (the first versions spent ~75 % of their issue slots on long-long div/mod).
+// max of two 16-byte vectors in their own type: the maximum of representable values is representable, so the packed 16-bit
+// compare gives the same bits as converting to fp32 and back (without the 24 conversions per load)
+template <typename T> __device__ __forceinline__ uint4 vmax16(uint4 a, uint4 b);
+template <> __device__ __forceinline__ uint4 vmax16<float>(uint4 a, uint4 b) {
+  return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))), __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))), __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+}
+template <> __device__ __forceinline__ uint4 vmax16<__half>(uint4 a, uint4 b) {
+  uint4 r;
+  const __half2* x = reinterpret_cast<const __half2*>(&a); const __half2* y = reinterpret_cast<const __half2*>(&b);
+  __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+template <> __device__ __forceinline__ uint4 vmax16<__nv_bfloat16>(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a); const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_maxpool(const T* __restrict__ in, T* __restrict__ out, int C, int Hin, int Hout) {
   constexpr int N = VecIO<T>::N;
@@ -258,22 +283,19 @@ __global__ void __launch_bounds__(256) k_maxpool(const T* __restrict__ in, T* __
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= Hpo * CV) return;
   const int xp = t / CV, cv = t - xp * CV, yp = blockIdx.y, b = blockIdx.z;
-  float m[N];
-#pragma unroll
-  for (int q = 0; q < N; ++q) m[q] = 0.f;
+  uint4 m = make_uint4(0u, 0u, 0u, 0u);                      // +0.0 in every type: the inputs are post-ReLU
   if (yp >= 1 && yp <= Hout && xp >= 1 && xp <= Hout) {
     const int y = yp - 1, x = xp - 1;                      // window rows 2y-1..2y+1 -> haloed 2y..2y+2
+    uint4 v[9];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        float v[N];
-        VecIO<T>::load(in + (((size_t)b * Hpi + 2 * y + dy) * Hpi + 2 * x + dx) * C + cv * N, v);
+      for (int dx = 0; dx < 3; ++dx)
+        v[dy * 3 + dx] = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * Hpi + 2 * y + dy) * Hpi + 2 * x + dx) * C + cv * N));
 #pragma unroll
-        for (int q = 0; q < N; ++q) m[q] = fmaxf(m[q], v[q]);
-      }
+    for (int i = 0; i < 9; ++i) m = vmax16<T>(m, v[i]);
   }
-  VecIO<T>::store(out + (((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N, m);
+  *reinterpret_cast<uint4*>(out + (((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N) = m;
 }
 
 int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, cudaStream_t s) {
@@ -288,6 +310,8 @@ int launch_maxpool(const void* in, void* out, int dt, int B, int C, int Hin, int
 // parity split for stride-2 convs: plane (p,q)[y'][x'] = X[2y'+p][2x'+q] (0 outside), y' in
 // [-1, Hout], stored with the OUTPUT's haloed geometry.  nplanes = 4 (3x3 s2) or 1 (1x1 s2).
 // ------------------------------------------------------------------------------------------------
+// A pure copy: 16 raw bytes per thread (8 sixteen-bit or 4 fp32 channels), no conversion (the first version went through
+// VecIO's float unpack / clamp / repack and was instruction-issue bound at 76 %: profiles/r2_glue_kernels.txt).
 template <typename T>
 __global__ void __launch_bounds__(256) k_phase_split(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout,
                                                      long long plane_stride_rows) {
@@ -299,11 +323,9 @@ __global__ void __launch_bounds__(256) k_phase_split(const T* __restrict__ in, T
   const int pl = blockIdx.z / B, b = blockIdx.z - pl * B;
   const int p = pl >> 1, q = pl & 1;
   const int iy = 2 * (yp - 1) + p, ix = 2 * (xp - 1) + q;
-  float v[N];
-#pragma unroll
-  for (int e = 0; e < N; ++e) v[e] = 0.f;
-  if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) VecIO<T>::load(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + cv * N, v);
-  VecIO<T>::store(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N, v);
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + cv * N));
+  *reinterpret_cast<uint4*>(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N) = v;
 }
 
 int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
@@ -371,74 +393,184 @@ int launch_upsample_add(const void* coarse, void* fine, int dt, int B, int C, in
   return YB_OK;
 }
 
-// protonet: bilinear x2, align_corners=True (modules/yolact.py:43,:51)
+// protonet: bilinear x2, align_corners=True (modules/yolact.py:43,:51).
+// One block per 4 x 16 tile of (haloed) output pixels, all C channels, in two phases: (1) the vertical interpolation runs once per
+// (output row, source column) -- <= 4 x 10 per tile -- into an fp32 shared-memory buffer; (2) every output is one horizontal
+// interpolation of two of those.  k_bilinear (four 16-byte gathers, 32 conversions
+// and both interpolations per 16-byte output) spent 250 instructions per output vector and was issue-bound at 81 % with the DRAM
+// pipe at 25 % (profiles/r2_glue_kernels.txt); this form needs ~60.  Interpolation weights are those of k_bilinear / torch; the
+// vertical-first order changes fp32 rounding only.
+constexpr int kUpTY = 4, kUpTX = 16, kUpSX = 10;                        // output tile, source columns it can touch
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample2x_tile(const T* __restrict__ src, T* __restrict__ dst, int C, int Hs, int Hd, float scale) {
+  constexpr int N = VecIO<T>::N;
+  extern __shared__ __align__(16) uint8_t s_up[];
+  float* sv = reinterpret_cast<float*>(s_up);                          // [kUpTY][kUpSX][C] vertically interpolated, fp32
+  __shared__ int s_y0[kUpTY], s_y1[kUpTY], s_x0[kUpTX], s_x1[kUpTX];
+  __shared__ float s_ly0[kUpTY], s_ly1[kUpTY], s_lx0[kUpTX], s_lx1[kUpTX];
+  const int Hps = Hs + 2, Hpd = Hd + 2, CV = C / N;                    // 256 % CV == 0 (checked by the launcher)
+  const int ty0 = blockIdx.y * kUpTY, tx0 = blockIdx.x * kUpTX, b = blockIdx.z;
+  // valid (non-halo) output range of the tile, in haloed coordinates
+  const int vy0 = max(ty0, 1), vy1 = min(ty0 + kUpTY - 1, Hd), vx0 = max(tx0, 1), vx1 = min(tx0 + kUpTX - 1, Hd);
+  int sx0 = 0, nx = 0;
+  if (vy0 <= vy1 && vx0 <= vx1) {
+    int i0, i1; float l0, l1;
+    src_index(vx0 - 1, scale, true, Hs, sx0, i1, l0, l1);
+    src_index(vx1 - 1, scale, true, Hs, i0, i1, l0, l1); nx = i1 - sx0 + 1;
+  }
+  if (threadIdx.x < kUpTY) {                                           // per-row / per-column source indices (patch-relative) and weights
+    const int oy = ty0 + (int)threadIdx.x;
+    int y0 = -1, y1 = -1; float l0 = 0.f, l1 = 0.f;
+    if (oy >= 1 && oy <= Hd) src_index(oy - 1, scale, true, Hs, y0, y1, l0, l1);      // absolute source rows
+    s_y0[threadIdx.x] = y0; s_y1[threadIdx.x] = y1; s_ly0[threadIdx.x] = l0; s_ly1[threadIdx.x] = l1;
+  } else if (threadIdx.x >= 32 && threadIdx.x < 32 + kUpTX) {
+    const int k = (int)threadIdx.x - 32, ox = tx0 + k;
+    int x0 = -1, x1 = -1; float l0 = 0.f, l1 = 0.f;
+    if (ox >= 1 && ox <= Hd) { src_index(ox - 1, scale, true, Hs, x0, x1, l0, l1); x0 -= sx0; x1 -= sx0; }
+    s_x0[k] = x0; s_x1[k] = x1; s_lx0[k] = l0; s_lx1[k] = l1;
+  }
+  const int cv = (int)threadIdx.x % CV, sub = (int)threadIdx.x / CV, nsub = 256 / CV;   // nsub >= 8 (launcher: CV <= 32)
+  const T* sb = src + (size_t)b * Hps * Hps * C + cv * N;
+  __syncthreads();
+  {                                                                    // (1) vertical interpolation, once per (output row, source column):
+    constexpr int kIt = (kUpTY * kUpSX + 7) / 8;                       //     all loads of a thread's <= 5 entries are issued before the first use
+    uint4 ra[kIt], rc[kIt];
+    int slot[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int e = sub + it * nsub;
+      slot[it] = -1;
+      if (e < kUpTY * nx) {
+        const int r = e / nx, j = e - r * nx;
+        const int y0 = s_y0[r];
+        if (y0 >= 0) {
+          slot[it] = r * kUpSX + j;
+          ra[it] = __ldg(reinterpret_cast<const uint4*>(sb + ((size_t)(y0 + 1) * Hps + sx0 + j + 1) * C));
+          rc[it] = __ldg(reinterpret_cast<const uint4*>(sb + ((size_t)(s_y1[r] + 1) * Hps + sx0 + j + 1) * C));
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      if (slot[it] < 0) continue;
+      const int r = slot[it] / kUpSX;
+      float a[N], c[N], v[N];
+      VecIO<T>::load(reinterpret_cast<const T*>(&ra[it]), a);
+      VecIO<T>::load(reinterpret_cast<const T*>(&rc[it]), c);
+      const float l0 = s_ly0[r], l1 = s_ly1[r];
+#pragma unroll
+      for (int q = 0; q < N; ++q) v[q] = l0 * a[q] + l1 * c[q];
+      float* o = sv + (size_t)slot[it] * C + cv * 4;                   // [slot][N/4 planes][CV] float4: lanes touch consecutive 16-byte words
+#pragma unroll
+      for (int q = 0; q < N; q += 4) *reinterpret_cast<float4*>(o + (q / 4) * (CV * 4)) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+    }
+  }
+  __syncthreads();
+  for (int e = sub; e < kUpTY * kUpTX; e += nsub) {                    // (2) horizontal interpolation + store
+    const int r = e / kUpTX, k = e % kUpTX, oy = ty0 + r, ox = tx0 + k;
+    if (oy >= Hpd || ox >= Hpd) continue;
+    T* d = dst + (((size_t)b * Hpd + oy) * Hpd + ox) * C + cv * N;
+    float v[N];
+    const int x0 = s_x0[k];
+    if (x0 < 0 || s_y0[r] < 0) {                                       // halo
+#pragma unroll
+      for (int q = 0; q < N; ++q) v[q] = 0.f;
+    } else {
+      const float* p0 = sv + ((size_t)(r * kUpSX + x0)) * C + cv * 4;
+      const float* p1 = sv + ((size_t)(r * kUpSX + s_x1[k])) * C + cv * 4;
+      const float l0 = s_lx0[k], l1 = s_lx1[k];
+#pragma unroll
+      for (int q = 0; q < N; q += 4) {
+        const float4 f0 = *reinterpret_cast<const float4*>(p0 + (q / 4) * (CV * 4)), f1 = *reinterpret_cast<const float4*>(p1 + (q / 4) * (CV * 4));
+        v[q] = l0 * f0.x + l1 * f1.x; v[q + 1] = l0 * f0.y + l1 * f1.y; v[q + 2] = l0 * f0.z + l1 * f1.z; v[q + 3] = l0 * f0.w + l1 * f1.w;
+      }
+    }
+    VecIO<T>::store(d, v);
+  }
+}
+
 int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hin, cudaStream_t s) {
   const int Hout = 2 * Hin;
-  const int cv = C / (dt == DT_F32 ? 4 : 8);
-  dim3 grid(ceil_div((Hout + 2) * cv, 256), Hout + 2, B);
   const float scale = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
-  YB_DISPATCH_DT(dt, (k_bilinear<T, false, true><<<grid, 256, 0, s>>>((const T*)in, (T*)out, C, Hin, Hout, scale)));
+  const int cv = C / (dt == DT_F32 ? 4 : 8);
+  const size_t smem = (size_t)kUpTY * kUpSX * C * 4;
+  if (dt != DT_F32 && smem <= 100 * 1024 && C % 8 == 0 && 256 % cv == 0 && cv <= 32) {
+    static std::once_flag once;
+    static cudaError_t attr = cudaSuccess;
+    std::call_once(once, [] {
+      attr = cudaFuncSetAttribute(k_upsample2x_tile<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (attr == cudaSuccess) attr = cudaFuncSetAttribute(k_upsample2x_tile<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    });
+    YB_CHECK_CUDA(attr);
+    dim3 grid(ceil_div(Hout + 2, kUpTX), ceil_div(Hout + 2, kUpTY), B);
+    if (dt == DT_F16) k_upsample2x_tile<__half><<<grid, 256, smem, s>>>((const __half*)in, (__half*)out, C, Hin, Hout, scale);
+    else k_upsample2x_tile<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, C, Hin, Hout, scale);
+  } else {
+    dim3 grid(ceil_div((Hout + 2) * cv, 256), Hout + 2, B);
+    YB_DISPATCH_DT(dt, (k_bilinear<T, false, true><<<grid, 256, 0, s>>>((const T*)in, (T*)out, C, Hin, Hout, scale)));
+  }
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// head epilogue: per (image, pixel, anchor) -- one warp -- softmax over the class logits, copy
-// the box regression, tanh the mask coefficients, scattered to the reference's
+// head epilogue: per (image, pixel) -- one warp -- softmax over the class logits of its anchors, copy
+// the box regression, tanh the mask coefficients, written in the reference's
 // [B, A, C] / [B, A, 4] / [B, A, K] layout (modules/yolact.py:26-31,:155-163).
 // head row layout: [conf: R*C | box: R*4 | coef: R*K | pad]
 // ------------------------------------------------------------------------------------------------
-// Each warp handles kHeadItems consecutive (pixel, anchor) items and issues ALL their loads before the first reduction: with one
-// item per warp the kernel was latency-bound (a handful of loads in flight per warp, ~2 us per warp lifetime, 0.5 ms per forward).
-constexpr int kHeadItems = 4;
+// One warp per pixel: the pixel's head row (R*NC + R*4 + R*K <= ld floats, 16-byte aligned) is read with 128-bit loads into the
+// warp's shared-memory slice, the R softmaxes / tanh run from there, and the results leave as the pixel's R consecutive anchor rows --
+// contiguous runs of R*NC, R*4 and R*K floats in the outputs.  (The first version gave each warp one (pixel, anchor) item and read
+// its 81 + 4 + 32 values with partially filled, misaligned loads: 2.9 TB/s; profiles/r2_glue_kernels.txt.)
+constexpr int kHeadWarps = 8;
 
-__global__ void __launch_bounds__(256) k_head_finalize(const float* __restrict__ head, int ld, int HW, int R, int NC, int K,
-                                                       int anchor_offset, int A_total, float* __restrict__ cls,
-                                                       float* __restrict__ box, float* __restrict__ coef) {
-  const int lane = threadIdx.x & 31;
-  const int wi0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kHeadItems;  // first (pixel, anchor) item of this warp
-  const int n_items = HW * R;
-  if (wi0 >= n_items) return;
+__global__ void __launch_bounds__(kHeadWarps * 32) k_head_finalize(const float* __restrict__ head, int ld, int HW, int R, int NC, int K,
+                                                                   int anchor_offset, int A_total, float* __restrict__ cls,
+                                                                   float* __restrict__ box, float* __restrict__ coef) {
+  extern __shared__ float s_head[];                                    // [kHeadWarps][ld]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pix = blockIdx.x * kHeadWarps + w;
+  if (pix >= HW) return;
   const int b = blockIdx.y;
-  float lg[kHeadItems][4], bx[kHeadItems], cf[kHeadItems][2];          // NC <= 128, K <= 64
-  size_t arow[kHeadItems];
+  float* sr = s_head + (size_t)w * ld;
+  const float4* row4 = reinterpret_cast<const float4*>(head + ((size_t)b * HW + pix) * ld);
+  const int used4 = (R * (NC + 4 + K) + 3) >> 2;
+  for (int i = lane; i < used4; i += 32) reinterpret_cast<float4*>(sr)[i] = __ldg(row4 + i);
+  __syncwarp();
+  const size_t arow = (size_t)b * A_total + anchor_offset + (size_t)pix * R;   // first of the pixel's R anchors
+  for (int a = 0; a < R; ++a) {
+    float lg[4];
 #pragma unroll
-  for (int it = 0; it < kHeadItems; ++it) {
-    const int wi = min(wi0 + it, n_items - 1);                         // clamp: the tail warp recomputes its last item
-    const int pix = wi / R, a = wi - pix * R;
-    const float* row = head + ((size_t)b * HW + pix) * ld;
-    arow[it] = (size_t)b * A_total + anchor_offset + (size_t)pix * R + a;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const int c = lane + 32 * i; lg[it][i] = c < NC ? __ldg(row + a * NC + c) : -INFINITY; }
-    bx[it] = lane < 4 ? __ldg(row + R * NC + a * 4 + lane) : 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { const int k = lane + 32 * i; cf[it][i] = k < K ? __ldg(row + R * NC + R * 4 + a * K + k) : 0.f; }
-  }
-#pragma unroll
-  for (int it = 0; it < kHeadItems; ++it) {
-    if (wi0 + it >= n_items) break;
-    float mx = fmaxf(fmaxf(lg[it][0], lg[it][1]), fmaxf(lg[it][2], lg[it][3]));
+    for (int i = 0; i < 4; ++i) { const int c = lane + 32 * i; lg[i] = c < NC ? sr[a * NC + c] : -INFINITY; }
+    float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     float ex[4], sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { ex[i] = (lane + 32 * i) < NC ? __expf(lg[it][i] - mx) : 0.f; sum += ex[i]; }
+    for (int i = 0; i < 4; ++i) { ex[i] = (lane + 32 * i) < NC ? __expf(lg[i] - mx) : 0.f; sum += ex[i]; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     const float inv = 1.f / sum;
+    __syncwarp();                                                      // every lane has read this anchor's logits
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const int c = lane + 32 * i; if (c < NC) cls[arow[it] * NC + c] = ex[i] * inv; }
-    if (lane < 4) box[arow[it] * 4 + lane] = bx[it];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { const int k = lane + 32 * i; if (k < K) coef[arow[it] * K + k] = tanhf(cf[it][i]); }
+    for (int i = 0; i < 4; ++i) { const int c = lane + 32 * i; if (c < NC) sr[a * NC + c] = ex[i] * inv; }
   }
+  __syncwarp();
+  float* co = cls + arow * NC;
+  for (int i = lane; i < R * NC; i += 32) co[i] = sr[i];
+  if (lane < R * 4) box[arow * 4 + lane] = sr[R * NC + lane];
+  float* ko = coef + arow * K;
+  for (int i = lane; i < R * K; i += 32) ko[i] = tanhf(sr[R * NC + R * 4 + i]);
 }
 
 int launch_head_finalize(const float* head, int ld, int B, int HW, int R, int NC, int K, int anchor_offset, int A_total,
                          float* cls, float* box, float* coef, cudaStream_t s) {
-  YB_REQUIRE(NC <= 128 && K <= 64, YB_ERR_UNSUPPORTED, "head_finalize: num_classes=%d > 128 or coef_dim=%d > 64", NC, K);
-  dim3 grid(ceil_div(HW * R, 8 * kHeadItems), B);
-  k_head_finalize<<<grid, 256, 0, s>>>(head, ld, HW, R, NC, K, anchor_offset, A_total, cls, box, coef);
+  YB_REQUIRE(NC <= 128 && K <= 64 && R * 4 <= 32, YB_ERR_UNSUPPORTED, "head_finalize: num_classes=%d > 128, coef_dim=%d > 64 or %d ratios", NC, K, R);
+  YB_REQUIRE(ld % 4 == 0 && R * (NC + 4 + K) <= ld && (size_t)kHeadWarps * ld * 4 <= 48 * 1024, YB_ERR_UNSUPPORTED, "head_finalize: row stride %d", ld);
+  dim3 grid(ceil_div(HW, kHeadWarps), B);
+  k_head_finalize<<<grid, kHeadWarps * 32, (size_t)kHeadWarps * ld * 4, s>>>(head, ld, HW, R, NC, K, anchor_offset, A_total, cls, box, coef);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
