@@ -798,13 +798,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // a third of the ring and 12 % of the MMA time but was 20-50 % slower: 8 lane-divergent 16-byte loads per thread and chunk through
 // an L1 that the 220 KB of shared memory leave 28 KB of (profiles/r2_bneck_experiments.txt).
 // =================================================================================================================
-constexpr int BK_SLOTS = 5;
+constexpr int BK_MAX_SLOTS = 8;
 constexpr uint32_t BK_SLOT = 16384;
 
 struct BnParams {
   long long M;
   int m_tiles;              // pair tiles of 256 rows
   int Cmid, Cexp, nchunks, kbA;
+  int slots;                // ring depth (5..8 slots of 16 KB, whatever shared memory is left)
+  int t2_bufs;              // 2: the next tile's t2 is loaded while this one is in use (narrow layers are HBM-latency bound otherwise)
   unsigned long long* trace;  // tooling (YOLACT_B200_BNECK_TRACE): cycle stamps, see k_bneck_tc
   Geom g;
   const float* b3;
@@ -819,16 +821,16 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t rank = cluster_ctarank();
-  uint8_t* sT2 = smem;                                         // [kbA][128 rows x 128 B]
-  uint8_t* sX = sT2 + (size_t)p.kbA * TC_A_STAGE;              // [2 buffers][2 k-blocks][128 rows x 128 B]
-  uint8_t* sRing = sX + 4 * TC_A_STAGE;                        // [BK_SLOTS][16 KB]
-  uint8_t* sEye = sRing + (size_t)BK_SLOTS * BK_SLOT;          // [32 rows][128 B]: this CTA's half of the 64 x 64 identity
+  uint8_t* sT2 = smem;                                         // [t2_bufs][kbA][128 rows x 128 B]
+  uint8_t* sX = sT2 + (size_t)p.t2_bufs * p.kbA * TC_A_STAGE;  // [2 buffers][2 k-blocks][128 rows x 128 B]
+  uint8_t* sRing = sX + 4 * TC_A_STAGE;                        // [slots][16 KB]
+  uint8_t* sEye = sRing + (size_t)p.slots * BK_SLOT;          // [32 rows][128 B]: this CTA's half of the 64 x 64 identity
   float* sBias = reinterpret_cast<float*>(sEye + 4096);        // [Cexp] b3 then [Cmid] b1: read by every epilogue warp, every chunk
   uint64_t* full = reinterpret_cast<uint64_t*>(sBias + p.Cexp + p.Cmid);   // [8]
   uint64_t* empty = full + 8;                                  // [8]
-  uint64_t* t2_full = empty + 8;
-  uint64_t* t2_empty = t2_full + 1;
-  uint64_t* accA_full = t2_empty + 1;                          // [2]
+  uint64_t* t2_full = empty + 8;                               // [2]
+  uint64_t* t2_empty = t2_full + 2;                            // [2]
+  uint64_t* accA_full = t2_empty + 2;                          // [2]
   uint64_t* accA_empty = accA_full + 2;                        // [2]
   uint64_t* accB_full = accA_empty + 2;
   uint64_t* accB_empty = accB_full + 1;
@@ -843,7 +845,7 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW3) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
     for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(t2_full, 1); mbar_init(t2_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&t2_full[i], 1); mbar_init(&t2_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&accA_full[i], 1); mbar_init(&accA_empty[i], 16);
       mbar_init(&xs_full[i], 16); mbar_init(&xs_empty[i], 1);
@@ -886,7 +888,8 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
   // tooling: cycle stamps of the leader CTA of pair 0 (YOLACT_B200_BNECK_TRACE), 8 events x 64 chunks
   unsigned long long* const trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
   auto stamp = [&](int ev, uint32_t qq) { if (trace && qq < 64u) trace[ev * 64 + qq] = (unsigned long long)clock64(); };
-  const int nch = p.nchunks, kbA = p.kbA;
+  const int nch = p.nchunks, kbA = p.kbA, slots = p.slots;
+  const int kpb = kbA >= 2 ? 2 : 1;                                   // W3 k-blocks packed into one ring slot
   const uint32_t w1_bytes = (uint32_t)(p.Cmid / 2) * 128u;            // one W1 k-block of this CTA: Cmid/2 rows x 128 B
 
   if (warp == 0) {
@@ -894,22 +897,21 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
     if (lane == 0) {
       griddep_wait();
       int stage = 0; uint32_t phase = 0;
-      const uint32_t t2_full_addr = map_to_rank(smem_u32(t2_full), 0);
-      auto load_a = [&](int c, int row0) {                              // operands of A(c): W3 chunk (two k-blocks per slot), residual chunk
-        for (int s = 0; s < kbA / 2; ++s) {
+      auto load_a = [&](int c, int row0) {                              // operands of A(c): W3 chunk (kpb k-blocks per slot), residual chunk
+        for (int s = 0; s < kbA / kpb; ++s) {
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t fa = map_to_rank(smem_u32(&full[stage]), 0);
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * BK_SLOT);
-          for (int j = 0; j < 2; ++j)
-            tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT + (size_t)j * 8192, &tmW3, (2 * s + j) * TC_BK, c * 128 + (int)rank * 64, fa);
-          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+          if (rank == 0) mbar_expect_tx(&full[stage], 2u * (uint32_t)kpb * 8192u);
+          for (int j = 0; j < kpb; ++j)
+            tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT + (size_t)j * 8192, &tmW3, (kpb * s + j) * TC_BK, c * 128 + (int)rank * 64, fa);
+          if (++stage == slots) { stage = 0; phase ^= 1; }
         }
         for (int j = 0; j < 2; ++j) {
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t fa = map_to_rank(smem_u32(&full[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * BK_SLOT);
           tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT, &tmX, c * 128 + j * TC_BK, row0, fa);
-          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+          if (++stage == slots) { stage = 0; phase ^= 1; }
         }
       };
       auto load_b = [&](int c) {                                        // B operand of B(c): W1[:, c*128 .. +127], two k-blocks
@@ -918,14 +920,17 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
           const uint32_t fa = map_to_rank(smem_u32(&full[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * w1_bytes);
           tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT, &tmW1, c * 128 + kb * TC_BK, (int)rank * (p.Cmid / 2), fa);
-          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+          if (++stage == slots) { stage = 0; phase ^= 1; }
         }
       };
       for (int i = 0; unit + i * units < p.m_tiles; ++i) {
         const int row0 = (2 * (unit + i * units) + (int)rank) * TC_BM;
-        mbar_wait(t2_empty, (uint32_t)(i & 1) ^ 1u);                    // A(last) of the previous tile has read the t2 tile
-        if (rank == 0) mbar_expect_tx(t2_full, 2u * (uint32_t)kbA * TC_A_STAGE);
-        for (int kb = 0; kb < kbA; ++kb) tma_load_2d_pair(sT2 + (size_t)kb * TC_A_STAGE, &tmT2, kb * TC_BK, row0, t2_full_addr);
+        const int tb = i % p.t2_bufs;
+        const uint32_t tn = (uint32_t)(i / p.t2_bufs);                   // n-th use of this t2 buffer
+        mbar_wait(&t2_empty[tb], (tn & 1u) ^ 1u);                        // A(last) of the tile that used it before has read it
+        if (rank == 0) mbar_expect_tx(&t2_full[tb], 2u * (uint32_t)kbA * TC_A_STAGE);
+        const uint32_t t2_full_addr = map_to_rank(smem_u32(&t2_full[tb]), 0);
+        for (int kb = 0; kb < kbA; ++kb) tma_load_2d_pair(sT2 + ((size_t)tb * kbA + kb) * TC_A_STAGE, &tmT2, kb * TC_BK, row0, t2_full_addr);
         for (int c = 0; c < nch; ++c) {
           load_a(c, row0);
           if (c >= 1) load_b(c - 1);
@@ -960,32 +965,33 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) umma_pair(dB, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idescB, (c | kb | k) != 0 ? 1u : 0u, issue);
           umma_commit_pair(&empty[stage], issue);
-          if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+          if (++stage == slots) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&xs_empty[buf], issue);
       };
       for (int i = 0; unit + i * units < p.m_tiles; ++i) {
-        mbar_wait(t2_full, (uint32_t)(i & 1));
+        const int tb = i % p.t2_bufs;
+        mbar_wait(&t2_full[tb], (uint32_t)(i / p.t2_bufs) & 1u);
         tc_fence_after();
+        const uint8_t* sT2b = sT2 + (size_t)tb * kbA * TC_A_STAGE;
         for (int c = 0; c < nch; ++c, ++q) {
           const int a = (int)(q & 1u);
           if (lane == 0) stamp(0, q);
           mbar_wait(&accA_empty[a], ((q >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t dA = tmem_base + (uint32_t)(a * 128);
-          for (int s = 0; s < kbA / 2; ++s) {
+          for (int s = 0; s < kbA / kpb; ++s) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int kb = 2 * s + j;
-              const uint64_t da = umma_desc(smem_u32(sT2 + (size_t)kb * TC_A_STAGE));
+            for (int j = 0; j < kpb; ++j) {
+              const int kb = kpb * s + j;
+              const uint64_t da = umma_desc(smem_u32(sT2b + (size_t)kb * TC_A_STAGE));
               const uint64_t db = umma_desc(smem_u32(sRing + (size_t)stage * BK_SLOT + (size_t)j * 8192));
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) umma_pair(dA, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idescA, (kb | k) != 0 ? 1u : 0u, issue);
             }
             umma_commit_pair(&empty[stage], issue);
-            if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+            if (++stage == slots) { stage = 0; phase ^= 1; }
           }
           for (int j = 0; j < 2; ++j) {                                 // accA[:, 64j .. 64j+63] += x_j * I
             mbar_wait(&full[stage], phase);
@@ -995,11 +1001,11 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) umma_pair(dA + (uint32_t)(j * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idescE, 1u, issue);
             umma_commit_pair(&empty[stage], issue);
-            if (++stage == BK_SLOTS) { stage = 0; phase ^= 1; }
+            if (++stage == slots) { stage = 0; phase ^= 1; }
           }
           umma_commit_pair(&accA_full[a], issue);
           if (lane == 0) stamp(1, q);
-          if (c == nch - 1) umma_commit_pair(t2_empty, issue);
+          if (c == nch - 1) umma_commit_pair(&t2_empty[tb], issue);
           if (c >= 1) issue_b(c - 1, q - 1, i);
         }
         issue_b(nch - 1, q - 1, i);
@@ -1053,7 +1059,9 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
         tmem_ld32(t_addr, r0);
         tmem_ld32(t_addr + 32, r1);
         mbar_wait(&xs_empty[a], ((q >> 1) & 1u) ^ 1u);                  // B(q-2) has read this staging buffer
-        if (elected) bulk_wait_read<1>();                               // ... and so has this warp's TMA store of chunk q-2
+        if (elected) {                                                  // ... and so has this warp's TMA store of chunk q-2
+          if (c == 0) bulk_wait_read<0>(); else bulk_wait_read<1>();    //     (first chunk of a tile: E2 may have used this slab last)
+        }
         __syncwarp();
         tmem_ld_wait();
         if (warp == 2 && lane == 0) stamp(5, q);
@@ -1073,25 +1081,59 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
           if (warp == 2) stamp(6, q);
         }
       }
-      // ---- E2: t1 = relu(accB + b1), this warp's Cmid/2 columns in 64-column slabs (staging buffers 0 and 1 in turn) ----
+      // ---- E2: t1 = relu(accB + b1), this warp's Cmid/2 columns: 64-column slabs (staging buffers 0 and 1 in turn), or -- Cmid = 64 --
+      //      one 32-column piece in the 64-byte-swizzled form of k_conv_tc's epilogue ----
       mbar_wait(accB_full, (uint32_t)(i & 1));
       tc_fence_after();
-      for (int j = 0; j < p.Cmid / 128; ++j) {
-        uint32_t r0[32], r1[32];
-        const int col = grp * (p.Cmid / 2) + j * 64;
+      const int cw = p.Cmid / 2;
+      if (cw >= 64) {
+        for (int j = 0; j < cw / 64; ++j) {
+          uint32_t r0[32], r1[32];
+          const int col = grp * cw + j * 64;
+          tmem_ld32(t_lane + 256u + (uint32_t)col, r0);
+          tmem_ld32(t_lane + 256u + (uint32_t)col + 32u, r1);
+          if (elected) bulk_wait_read<1>();
+          __syncwarp();
+          tmem_ld_wait();
+          uint8_t* const slab = slab0 + (size_t)(j & 1) * 2 * TC_A_STAGE;
+          uint8_t* row = slab + lane * 128;
+          piece(r0, sBias + p.Cexp + col, zero_row, row, 0);
+          piece(r1, sBias + p.Cexp + col + 32, zero_row, row, 1);
+          fence_async_smem();
+          __syncwarp();
+          if (elected) {
+            tma_store_2d(&tmT1, slab, col, row0);
+            bulk_commit();
+          }
+        }
+      } else {
+        uint32_t r0[32];
+        const int col = grp * 32;
         tmem_ld32(t_lane + 256u + (uint32_t)col, r0);
-        tmem_ld32(t_lane + 256u + (uint32_t)col + 32u, r1);
         if (elected) bulk_wait_read<1>();
         __syncwarp();
         tmem_ld_wait();
-        uint8_t* const slab = slab0 + (size_t)(j & 1) * 2 * TC_A_STAGE;
-        uint8_t* row = slab + lane * 128;
-        piece(r0, sBias + p.Cexp + col, zero_row, row, 0);
-        piece(r1, sBias + p.Cexp + col + 32, zero_row, row, 1);
+        const float* bias = sBias + p.Cexp + col;
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + e);
+          pk[e / 2] = pack2_sat<F16, true>(__uint_as_float(r0[e]) + bb.x, __uint_as_float(r0[e + 1]) + bb.y);
+          pk[e / 2 + 1] = pack2_sat<F16, true>(__uint_as_float(r0[e + 2]) + bb.z, __uint_as_float(r0[e + 3]) + bb.w);
+        }
+        if (zero_row) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] = 0u;
+        }
+        const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);             // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8]
+        uint8_t* row = slab0 + lane * 64;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          *reinterpret_cast<uint4*>(row + (((uint32_t)jj ^ sw64) << 4)) = make_uint4(pk[jj * 4], pk[jj * 4 + 1], pk[jj * 4 + 2], pk[jj * 4 + 3]);
         fence_async_smem();
         __syncwarp();
         if (elected) {
-          tma_store_2d(&tmT1, slab, col, row0);
+          tma_store_2d(&tmT1, slab0, col, row0);
           bulk_commit();
         }
       }
@@ -1405,14 +1447,25 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
 // ---- fused bottleneck tail (k_bneck_tc) ------------------------------------------------------------------------------
 struct BnPlan {
   CUtensorMap tmT2, tmX, tmW3, tmW1, tmXo, tmT1;
-  int sms, Cmid, Cexp;
+  int sms, Cmid, Cexp, slots, t2_bufs;
   size_t smem_bytes;
 };
 
 bool bneck_supported(int act_dt, int Cmid, int Cexp) {
-  // Cmid = 256: accB fills the 256 TMEM columns next to the two 128-column accA buffers, and E2's two 64-column slabs per warp
-  // keep the staging buffers alternating (the bulk-group accounting of the epilogue relies on it)
-  return (act_dt == DT_F16 || act_dt == DT_BF16) && Cmid == 256 && Cexp % 256 == 0 && Cexp >= 256 && !getenv("YOLACT_B200_NO_FUSE");
+  // Cmid <= 256: accB (Cmid columns) sits next to the two 128-column accA buffers in the 512 TMEM columns; Cexp / 128 chunks must be
+  // even (accumulator / staging buffers alternate by chunk parity across tiles)
+  return (act_dt == DT_F16 || act_dt == DT_BF16) && (Cmid == 64 || Cmid == 128 || Cmid == 256) && Cexp == 4 * Cmid && !getenv("YOLACT_B200_NO_FUSE");
+}
+
+// shared-memory plan: [t2 buffers][x' staging 64 KB][ring][identity 4 KB][biases][barriers]
+static void bneck_smem(int Cmid, int Cexp, int* slots, int* t2_bufs, size_t* bytes) {
+  const size_t t2 = (size_t)(Cmid / 64) * TC_A_STAGE;
+  const size_t fixed = 1024 + 4 * TC_A_STAGE + 4096 + (size_t)(Cexp + Cmid) * 4 + 1024;
+  const size_t budget = 227 * 1024;
+  *t2_bufs = (fixed + 2 * t2 + 5 * BK_SLOT <= budget) ? 2 : 1;
+  int n = (int)((budget - fixed - (size_t)*t2_bufs * t2) / BK_SLOT);
+  *slots = n > BK_MAX_SLOTS ? BK_MAX_SLOTS : n;
+  *bytes = fixed + (size_t)*t2_bufs * t2 + (size_t)*slots * BK_SLOT;
 }
 
 int bneck_plan_create(const BneckArgs& a, int max_batch, BnPlan** out) {
@@ -1426,11 +1479,12 @@ int bneck_plan_create(const BneckArgs& a, int max_batch, BnPlan** out) {
   if (s == YB_OK) s = make_map(&pl->tmW3, a.w3, (uint64_t)a.Cmid, (uint64_t)a.Cexp, 64, f16);
   if (s == YB_OK) s = make_map(&pl->tmW1, a.w1, (uint64_t)a.Cexp, (uint64_t)a.Cmid, (uint32_t)(a.Cmid / 2), f16);
   if (s == YB_OK) s = make_map(&pl->tmXo, a.xo, (uint64_t)a.Cexp, rows, 32, f16);
-  if (s == YB_OK) s = make_map(&pl->tmT1, a.t1, (uint64_t)a.Cmid, rows, 32, f16);
+  if (s == YB_OK) s = a.Cmid >= 128 ? make_map(&pl->tmT1, a.t1, (uint64_t)a.Cmid, rows, 32, f16)
+                                    : make_map(&pl->tmT1, a.t1, (uint64_t)a.Cmid, rows, 32, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (s == YB_OK) s = tc_device_setup(&pl->sms);
   if (s != YB_OK) { delete pl; return s; }
-  pl->smem_bytes = 1024 + (size_t)(a.Cmid / 64) * TC_A_STAGE + 4 * TC_A_STAGE + (size_t)BK_SLOTS * BK_SLOT + 4096 + (size_t)(a.Cexp + a.Cmid) * 4 + 1024;
-  YB_REQUIRE(pl->smem_bytes <= 227 * 1024, YB_ERR_UNSUPPORTED, "bneck_plan_create: %zu bytes of shared memory", pl->smem_bytes);
+  bneck_smem(a.Cmid, a.Cexp, &pl->slots, &pl->t2_bufs, &pl->smem_bytes);
+  YB_REQUIRE(pl->slots >= 5 && pl->smem_bytes <= 227 * 1024, YB_ERR_UNSUPPORTED, "bneck_plan_create: %zu bytes of shared memory, %d slots", pl->smem_bytes, pl->slots);
   *out = pl;
   return YB_OK;
 }
@@ -1444,6 +1498,7 @@ int launch_bneck_tc(const BnPlan* pl, const BneckArgs& a, cudaStream_t s) {
   p.M = (long long)a.B * a.g.plane();
   p.m_tiles = (int)((p.M + 2 * TC_BM - 1) / (2 * TC_BM));
   p.Cmid = a.Cmid; p.Cexp = a.Cexp; p.nchunks = a.Cexp / 128; p.kbA = a.Cmid / 64;
+  p.slots = pl->slots; p.t2_bufs = pl->t2_bufs;
   p.g = a.g; p.b3 = a.b3; p.b1 = a.b1;
   p.trace = nullptr;
   if (getenv("YOLACT_B200_BNECK_TRACE")) {
