@@ -297,6 +297,19 @@ def mask_stage_leg(dev, pk, img_size=550, img_h=480, img_w=640, reps=20):
         ms = cuda_time(lambda i: after_nms(*args, mask_dtype=dt), reps)
         wbytes = d * img_h * img_w * bpp
         out[name] = {'ms_per_image': ms, 'mask_bytes_per_image': wbytes, 'write_gbs': wbytes / (ms * 1e-3) / 1e9, 'frac_of_hbm_peak': wbytes / (ms * 1e-3) / 1e9 / pk['hbm']}
+        try:                                                        # the same call replayed from a CUDA graph: device time without the Python / launch gaps
+            g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                after_nms(*args, mask_dtype=dt)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, stream=st):
+                    keep = after_nms(*args, mask_dtype=dt)
+            torch.cuda.synchronize()
+            gms = cuda_time(lambda i: g.replay(), reps)
+            out[name].update({'graph_ms_per_image': gms, 'graph_write_gbs': wbytes / (gms * 1e-3) / 1e9, 'graph_frac_of_hbm_peak': wbytes / (gms * 1e-3) / 1e9 / pk['hbm']})
+            del g, keep
+        except Exception as e:
+            out[name]['graph_error'] = repr(e)[:200]
     bits = after_nms(*args, mask_dtype='bits')[3]
     gt = bits[:20].contiguous()
     for _ in range(3):
@@ -621,6 +634,21 @@ def run_ours(args):
                 'share_of_forward': tc['ms'] / total_ms if total_ms else None,
                 'alg_flops_per_launch': tc['flops'] / max(1, tc['launches']),
                 'avg_launch_ms': tc['ms'] / max(1, tc['launches']), 'timing': 'CUDA events per launch, separate profiling pass (3 steps)'}
+    roofline_fused = None
+    fz = prof.get('bneck_tc')
+    if fz and fz['launches']:
+        fa = fz['flops'] / (fz['ms'] * 1e-3) / 1e12
+        ft_ = None
+        if os.path.exists(tpath) and (ARCH, IMG, BATCH) == ('res101', 550, 64):
+            ft_ = (json.load(open(tpath)).get('fused') or {}).get('dram_bytes_per_launch_avg')
+        roofline_fused = {'kernel': 'k_bneck_tc (conv3 + residual + ReLU of a bottleneck chained into the next block\'s conv1 through shared memory)',
+                          'bound': 'tensor', 'achieved': fa, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': fa / pk['tf_sustained'],
+                          'traffic': ft_, 'alg_bytes_per_launch': fz['bytes'] / fz['launches'], 'alg_flops_per_launch': fz['flops'] / fz['launches'],
+                          'launches_per_step': fz['launches'] / max(1, fz['forwards']), 'avg_launch_ms': fz['ms'] / fz['launches'],
+                          'share_of_forward': fz['ms'] / total_ms if total_ms else None,
+                          'hbm_gbs': fz['bytes'] / (fz['ms'] * 1e-3) / 1e9, 'hbm_frac': fz['bytes'] / (fz['ms'] * 1e-3) / 1e9 / pk['hbm']}
+        both = (tc['flops'] + fz['flops']) / ((tc['ms'] + fz['ms']) * 1e-3) / 1e12
+        roofline['tcgen05_kernels_together'] = {'achieved': both, 'frac': both / pk['tf_sustained'], 'share_of_forward': (tc['ms'] + fz['ms']) / total_ms}
     breakdown = {k: {'ms_per_step': v['ms'] / max(1, v['forwards']), 'launches_per_step': v['launches'] / max(1, v['forwards']),
                      'alg_tflops': (v['flops'] / (v['ms'] * 1e-3) / 1e12) if v['ms'] and v['flops'] else None,
                      'alg_gbs': (v['bytes'] / (v['ms'] * 1e-3) / 1e9) if v['ms'] else None}
@@ -639,7 +667,7 @@ def run_ours(args):
                        'l2_policy': 'inputs (232 MB/step, two alternating batches) larger than the 126 MB L2'},
             'tensor_frac_of_peak': value * GFLOP_PER_IMG * 1e9 / (world * pk['tf_sustained'] * 1e12),
             'gflop_per_img': GFLOP_PER_IMG,
-            'fast_nms_us_per_img': nms_us, 'roofline': roofline, 'roofline_postprocess': pp_roof, 'kernel_breakdown': breakdown,
+            'fast_nms_us_per_img': nms_us, 'roofline': roofline, 'roofline_fused': roofline_fused, 'roofline_postprocess': pp_roof, 'kernel_breakdown': breakdown,
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity': parity}
     if other_scaling:
         line[other_scaling['scaling'] + '_scaling'] = other_scaling

@@ -39,6 +39,11 @@ def main(path, out_json='profiles/r2_traffic.json', out_txt='profiles/r2_ncu_tra
     js = {'kernel': 'k_conv_tc', 'source': f'{out_txt} (ncu dram__bytes_read.sum + dram__bytes_write.sum over ALL {n} k_conv_tc launches of the timed step(s) inside bench.py, res101@550 B=64 fp16)',
           'launches': n, 'dram_bytes_per_launch_avg': sum(a[2] + a[3] for a in conv) / max(1, n),
           'dram_read_bytes_total': sum(a[2] for a in conv), 'dram_write_bytes_total': sum(a[3] for a in conv)}
+    fused = [a for k, a in agg.items() if k.startswith('k_bneck_tc')]
+    nf = sum(a[0] for a in fused)
+    if nf:
+        js['fused'] = {'kernel': 'k_bneck_tc', 'launches': nf, 'dram_bytes_per_launch_avg': sum(a[2] + a[3] for a in fused) / nf,
+                       'dram_read_bytes_total': sum(a[2] for a in fused), 'dram_write_bytes_total': sum(a[3] for a in fused)}
     json.dump(js, open(out_json, 'w'), indent=1)
     print(json.dumps(js))
 

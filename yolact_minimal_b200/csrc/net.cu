@@ -921,9 +921,10 @@ int check_host_call(yb_net* net, int batch, const yb_detect_params* p, const cha
 }
 
 // forward + post-process of net->d_img on stream s (captured into a CUDA graph per (batch, params))
-int run_device_pipeline(yb_net* net, int batch, const yb_detect_params* p, bool want_coef, cudaStream_t s) {
+// `img`: device image batch the forward reads (net->d_img, or a submission slot's staging buffer: one graph per buffer)
+int run_device_pipeline(yb_net* net, const float* img, int batch, const yb_detect_params* p, bool want_coef, cudaStream_t s) {
   auto run = [&]() -> int {
-    YB_PROPAGATE(yb_net_forward(net, net->d_img, batch, net->d_cls, net->d_box, net->d_coef, net->d_proto, s));
+    YB_PROPAGATE(yb_net_forward(net, img, batch, net->d_cls, net->d_box, net->d_coef, net->d_proto, s));
     YB_PROPAGATE(yb_detect(net->d_cls, net->d_box, net->d_coef, net->d_anchors, batch, net->A, p, net->d_ws, net->ws_bytes, net->d_cnt,
                            net->d_ocls, net->d_oanc, net->d_osc, net->d_obox, want_coef ? net->d_ocoef : nullptr, s));
     return YB_OK;
@@ -931,7 +932,7 @@ int run_device_pipeline(yb_net* net, int batch, const yb_detect_params* p, bool 
   if (net->profiling || getenv("YOLACT_B200_NO_GRAPH")) return run();
   // ~150 kernel launches per call: capture once per (batch, params), replay afterwards
   std::string key((const char*)p, sizeof(*p));
-  key += std::to_string(batch) + (want_coef ? "c" : "n");
+  key += std::to_string(batch) + (want_coef ? "c" : "n") + std::to_string((unsigned long long)(uintptr_t)img);
   auto it = net->host_graphs.find(key);
   if (it == net->host_graphs.end()) {
     YB_PROPAGATE(run());                                         // warm run: lazy one-time setup stays outside the capture
@@ -966,7 +967,7 @@ extern "C" int yb_net_detect_host(yb_net* net, const float* img_host, int batch,
   const size_t K = net->cfg.coef_dim, S = net->cfg.img_size, D = p->max_det, b = batch;
   cudaStream_t s = net->own_stream;
   YB_CHECK_CUDA(cudaMemcpyAsync(net->d_img, img_host, b * 3 * S * S * 4, cudaMemcpyHostToDevice, s));
-  YB_PROPAGATE(run_device_pipeline(net, batch, p, out_coef != nullptr, s));
+  YB_PROPAGATE(run_device_pipeline(net, net->d_img, batch, p, out_coef != nullptr, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_count, net->d_cnt, b * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_class, net->d_ocls, b * D * 4, cudaMemcpyDeviceToHost, s));
   YB_CHECK_CUDA(cudaMemcpyAsync(out_anchor, net->d_oanc, b * D * 4, cudaMemcpyDeviceToHost, s));
@@ -997,8 +998,7 @@ extern "C" int yb_net_submit_host(yb_net* net, const float* img_host, int batch,
   YB_CHECK_CUDA(cudaEventRecord(sl.h2d, net->copy_stream));
   cudaStream_t s = net->own_stream;
   YB_CHECK_CUDA(cudaStreamWaitEvent(s, sl.h2d, 0));
-  YB_CHECK_CUDA(cudaMemcpyAsync(net->d_img, sl.d_stage, b * 3 * S * S * 4, cudaMemcpyDeviceToDevice, s));
-  YB_PROPAGATE(run_device_pipeline(net, batch, p, true, s));
+  YB_PROPAGATE(run_device_pipeline(net, sl.d_stage, batch, p, true, s));     // the forward reads the slot's staging buffer directly
   char* h = (char*)sl.h_res;
   YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_cnt, b * 4, cudaMemcpyDeviceToHost, s)); h += B * 4;
   YB_CHECK_CUDA(cudaMemcpyAsync(h, net->d_ocls, b * D * 4, cudaMemcpyDeviceToHost, s)); h += B * 256 * 4;

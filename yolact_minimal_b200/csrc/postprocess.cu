@@ -195,7 +195,18 @@ k_filter_decode(const float* __restrict__ cls, const float* __restrict__ box, co
 
   const float* src = cls + ((size_t)b * A + a0) * C;
   const int nelem = na * C;
-  for (int i = tid; i < nelem; i += kThreads) tile[i] = __ldcs(src + i);   // streamed once
+  {  // streamed once, 16 bytes per load where the tile's first element allows it (scalar head / tail: C is odd, A arbitrary)
+    const int head = min(nelem, (int)((4 - ((((size_t)b * A + a0) * C) & 3)) & 3));
+    const int nvec = (nelem - head) >> 2;
+    if (tid < head) tile[tid] = __ldcs(src + tid);
+    const float4* src4 = reinterpret_cast<const float4*>(src + head);
+    for (int i = tid; i < nvec; i += kThreads) {
+      const float4 v = __ldcs(src4 + i);
+      if (head == 0) reinterpret_cast<float4*>(tile)[i] = v;
+      else { float* t = tile + head + 4 * i; t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w; }
+    }
+    for (int i = head + 4 * nvec + tid; i < nelem; i += kThreads) tile[i] = __ldcs(src + i);
+  }
   __syncthreads();
 
   // two threads per anchor: even/odd class columns (bank-conflict-free for odd C)
