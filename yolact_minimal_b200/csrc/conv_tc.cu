@@ -47,6 +47,8 @@ constexpr uint32_t TC_WARP_TILE = 32 * 32 * 2;  // 2 KiB: one warp's 32 rows x 3
 constexpr uint32_t TC_A_STAGE = TC_BM * TC_BK * 2;   // 16 KiB
 constexpr uint32_t TC_SLAB_ROWS = TC_BM + 2;         // slab mode: rows m0-1 .. m0+128 of one tap row
 constexpr uint32_t TC_A_SLAB = 136 * TC_BK * 2;      // 17 KiB slot: the 130-row slab padded to the 1 KiB swizzle period
+constexpr uint32_t TC_S16_ROWS = TC_BM + 3;          // stem16: pixels p-1 .. p+129 of one tap row serve dx = 0 .. 3
+constexpr uint32_t TC_S16_SLOT = 5120;               // 131 rows x 32 B, padded to 1 KiB
 
 struct TcParams {
   long long M;            // rows to produce (B * plane)
@@ -71,6 +73,9 @@ struct TcParams {
   int res_kb;             // > 0: the residual is added BY THE TENSOR CORE: BN/64 extra k-blocks whose A tile is the
                           // residual's [128 x 64] slab and whose B tile is a shared-memory 64x64 identity (N=64 MMAs
                           // into the matching 64 accumulator columns) -- the epilogue never touches the residual
+  int stem16;             // stem form: A rows are single s2d pixels (16 channels = 32 bytes, SWIZZLE_32B); one [131 x 32 B] slab per tap row dy
+                          // serves the four dx taps through descriptors that start 0 / 32 / 64 / 96 B into it (K = 16 per MMA), the 16 weight
+                          // tiles [64 x 32 B] stay resident.  A quarter of the L2 -> shared-memory fill of the overlapping-rows form.
   int gemm;               // plain GEMM over long K (weight gradients): out[M x taps*Nper] (+)= A[M x K] * B_tap[Nper x K]^T with both operands
                           // K-major; N tile n -> tap n / gemm_ntile_tap, B rows (n % gemm_ntile_tap) * BN, B columns k + gemm_shift[tap]
                           // (the conv tap as a COLUMN offset of the transposed activations; out-of-range columns read as zero)
@@ -87,7 +92,7 @@ struct TcParams {
 
 struct TcPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  int BN, stages, tmem_cols, tma_epi, nres, b_resident, res_kb, pair, slab, stages_a, alt_tiles;
+  int BN, stages, tmem_cols, tma_epi, nres, b_resident, res_kb, pair, slab, stages_a, alt_tiles, stem16;
   int sms;                 // SM count of the device the plan was created on
   int gemm;                // plain-GEMM plan (tc_plan_create_gemm)
   size_t smem_bytes;
@@ -187,6 +192,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
   d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+// K-major, 32B-swizzled operand tile (stem16): rows of 32 bytes (K = 16), 8-row groups 256 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                             // SWIZZLE_32B
   return d;
 }
 // MN-major, 128B-swizzled operand tile (the weight-gradient GEMM's B operand, read straight from the [pixels][channels] activations):
@@ -379,10 +394,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024B alignment
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                              // CTA pair: 0 = leader (issues the MMAs)
   const int bn_cta = PAIR ? p.BN / 2 : p.BN;                                        // weight rows held by this CTA
-  const uint32_t b_stage = (uint32_t)bn_cta * TC_BK * 2;
-  const int num_kb = p.ntaps * p.kb_per_tap;
+  const uint32_t b_stage = p.stem16 ? 2048u : (uint32_t)bn_cta * TC_BK * 2;         // stem16: 64 rows x 32 B per (dy, dx) weight tile
+  const int num_kb = p.stem16 ? 16 : p.ntaps * p.kb_per_tap;
   uint8_t* sA = smem;                                                               // [stages][16 KiB]
-  uint8_t* sB = smem + (p.slab ? (size_t)p.stages_a * TC_A_SLAB : (size_t)p.stages * TC_A_STAGE);   // [stages | num_kb][BN x 128 B]
+  uint8_t* sB = smem + (p.stem16 ? (size_t)p.stages_a * TC_S16_SLOT : p.slab ? (size_t)p.stages_a * TC_A_SLAB : (size_t)p.stages * TC_A_STAGE);   // [stages | num_kb][BN x 128 B]
   uint8_t* sOut = sB + (size_t)(p.b_resident ? num_kb : p.stages) * b_stage;        // [8 warps][2][32 rows x 64 B], SWIZZLE_64B
   uint8_t* sRes = sOut + (p.tma_epi ? 8 * TC_OUT_BUFS * TC_WARP_TILE : 0);          // [8 warps][nres][32 rows x 64 B]
   uint8_t* sEye = sRes;                                                             // res_kb: [64][128 B] identity, 128B-swizzled
@@ -455,7 +470,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // expects both CTAs' bytes (the leader's MMAs read both shared memories); each CTA recycles a stage on its own
       // `empty` barrier (the MMA commit is multicast to both)
       const uint32_t bfull_addr = PAIR ? map_to_rank(smem_u32(b_full), 0) : 0u;
-      if (p.b_resident && tile_at<PAIR>(p, 0, m_tile, n_tile)) {
+      if (p.stem16 && tile_at<PAIR>(p, 0, m_tile, n_tile)) {          // 16 weight tiles [64 x 16], k = dy*64 + dx*16
+        mbar_expect_tx(b_full, 16u * b_stage);
+        for (int j = 0; j < 16; ++j) tma_load_2d(sB + (size_t)j * b_stage, &tmB, j * 16, 0, b_full);
+      } else if (p.b_resident && tile_at<PAIR>(p, 0, m_tile, n_tile)) {
         // the CTA's whole weight slice [bn_cta x Ktot], loaded once
         if (!PAIR || rank == 0) mbar_expect_tx(b_full, (uint32_t)num_kb * b_stage * (PAIR ? 2u : 1u));
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -467,6 +485,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = (p.b_resident ? TC_A_STAGE : TC_A_STAGE + b_stage) * (PAIR ? 2u : 1u);
       int sa = 0; uint32_t phase_a = 0;
+      for (int i = 0; p.stem16 && tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
+        for (int dy = 0; dy < 4; ++dy) {                               // one [131 px x 16 ch] slab per tap row
+          mbar_wait(&empty_a[sa], phase_a ^ 1);
+          mbar_expect_tx(&full_a[sa], TC_S16_ROWS * 32);
+          tma_load_2d(sA + (size_t)sa * TC_S16_SLOT, &tmA, 0, m_tile * TC_BM + p.tap_shift[dy], &full_a[sa]);
+          if (++sa == p.stages_a) { sa = 0; phase_a ^= 1; }
+        }
+      }
       for (int i = 0; p.slab && tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
         // slab mode: per (tap row dy, k-block) one A slab, then the three dx weight tiles that consume it
         const int m0 = m_tile * TC_BM, n0 = n_tile * p.BN;
@@ -497,7 +523,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
       }
-      for (int i = 0; !p.slab && tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
+      for (int i = 0; !p.slab && !p.stem16 && tile_at<PAIR>(p, i, m_tile, n_tile); ++i) {
         const int m0 = m_tile * TC_BM;
         int n0 = n_tile * p.BN, bcol0 = 0;
         if (p.gemm) {                                              // B tile: rows of the tap's operand, columns shifted by the tap
@@ -557,6 +583,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        if (p.stem16) {
+          for (int dy = 0; dy < 4; ++dy) {
+            mbar_wait(&full_a[sa], phase_a);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + (size_t)sa * TC_S16_SLOT);
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx)                                        // tap dx = slab rows dx .. dx+127, K = 16
+              umma_bf16(d_tmem, umma_desc_sw32(a_addr + (uint32_t)dx * 32u), umma_desc_sw32(smem_u32(sB + (size_t)(dy * 4 + dx) * b_stage)), idesc,
+                        (dy | dx) != 0 ? 1u : 0u, issue);
+            umma_commit(&empty_a[sa], issue);
+            if (++sa == p.stages_a) { sa = 0; phase_a ^= 1; }
+          }
+        }
         if (p.slab) {
           int kbi = 0;
           for (int dy = 0; dy < 3; ++dy) {
@@ -585,7 +624,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         int kb_lo = 0, kb_hi = num_kb;
         if (p.gemm) gemm_kb_range(p, i, kb_lo, kb_hi);
-        for (int kb = kb_lo; kb < kb_hi && !p.slab; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi && !p.slab && !p.stem16; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t da = umma_desc(smem_u32(sA + (size_t)stage * TC_A_STAGE));
@@ -1253,8 +1292,12 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   size_t epi_bytes = pl->tma_epi ? (size_t)8 * (TC_OUT_BUFS + pl->nres) * TC_WARP_TILE : 0;
   if (pl->res_kb) epi_bytes += 8192;                               // identity operand tile
   pl->alt_tiles = (pl->BN <= 64 && pl->nres == 0 && !getenv("YOLACT_B200_NO_ALT")) ? 1 : 0;
+  // stem (net.cu: 4 tap rows over the space-to-depth image, rows overlapping at 16 of 64 channels): the 32-byte-row form
+  pl->stem16 = (a.in_row_stride == 16 && a.Cin == 64 && a.Cin_pad == 64 && a.ntaps == 4 && pl->BN == 64 && !pl->pair && !a.residual &&
+                !getenv("YOLACT_B200_NO_STEM16")) ? 1 : 0;
   // slab mode (3x3, stride 1: the three dx taps of a tap row are consecutive rows of the same matrix)
   pl->slab = (a.ntaps == 9 && !pl->res_kb && !getenv("YOLACT_B200_NO_SLAB")) ? 1 : 0;
+  if (pl->stem16) pl->slab = 0;
   for (int dy = 0; dy < 3 && pl->slab; ++dy)
     for (int dx = 1; dx < 3; ++dx)
       if (a.tap_shift[3 * dy + dx] != a.tap_shift[3 * dy] + dx) pl->slab = 0;
@@ -1278,6 +1321,10 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
     pl->smem_bytes = (size_t)pl->stages_a * a_slot + (size_t)stages * b_stage + epi_bytes + 1024 + 1024;
     if (stages < 3) { pl->slab = 0; pl->stages_a = 0; }
   }
+  if (pl->stem16) {                                                // 16 resident weight tiles of 2 KB, 8 slab slots of 5 KB
+    pl->b_resident = 1; pl->stages = 1; pl->stages_a = 8;
+    pl->smem_bytes = (size_t)8 * TC_S16_SLOT + 16 * 2048 + epi_bytes + 1024 + 1024;
+  }
   if (!pl->b_resident && !pl->slab) {
     const size_t per_stage = TC_A_STAGE + b_stage;
     int stages = (int)((budget - epi_bytes) / per_stage);
@@ -1287,8 +1334,10 @@ int tc_plan_create(const ConvArgs& a, int max_batch, TcPlan** out) {
   const int Ktot = a.ntaps * a.Cin_pad;
   const int cout_alloc = (a.Cout_pad + 63) / 64 * 64;
   const bool f16 = a.act_dt == DT_F16;
-  int s = make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, pl->slab ? TC_SLAB_ROWS : TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.in_row_stride);
-  if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN), f16, TC_BK,
+  int s = pl->stem16 ? make_map(&pl->tmA, a.in, 16, (uint64_t)a.in_rows + 4, TC_S16_ROWS, f16, 16, CU_TENSOR_MAP_SWIZZLE_32B)
+                     : make_map(&pl->tmA, a.in, (uint64_t)a.Cin, (uint64_t)a.in_rows, pl->slab ? TC_SLAB_ROWS : TC_BM, f16, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.in_row_stride);
+  if (s == YB_OK && pl->stem16) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, 64, f16, 16, CU_TENSOR_MAP_SWIZZLE_32B, (uint64_t)a.w_ld);
+  else if (s == YB_OK) s = make_map(&pl->tmB, a.weight, (uint64_t)Ktot, (uint64_t)cout_alloc, (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN), f16, TC_BK,
                                CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)a.w_ld);
   pl->tmOut = pl->tmA; pl->tmRes = pl->tmA;                      // placeholders when the TMA epilogue is off
   if (s == YB_OK && pl->tma_epi) {
@@ -1405,7 +1454,7 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
   for (int i = 0; i < kMaxTaps; ++i) p.tap_shift[i] = a.tap_shift[i];
   p.BN = pl->BN; p.tmem_cols = pl->tmem_cols; p.stages = pl->stages;
   p.Cout = a.Cout; p.Cout_pad = a.Cout_pad; p.relu = a.relu; p.out_mode = a.out_mode;
-  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a; p.alt_tiles = pl->alt_tiles;
+  p.g = a.g; p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.is_f16 = a.act_dt == DT_F16; p.tma_epi = pl->tma_epi; p.nres = pl->nres; p.b_resident = pl->b_resident; p.res_kb = pl->res_kb; p.slab = pl->slab; p.stages_a = pl->stages_a; p.alt_tiles = pl->alt_tiles; p.stem16 = pl->stem16;
   p.gemm = 0; p.gemm_ntile_tap = 1; p.accumulate = 0; p.gemm_splits = 1; p.gemm_kb_split = 0;
   for (int i = 0; i < 16; ++i) p.gemm_shift[i] = 0;
   const int sms = pl->sms;
