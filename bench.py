@@ -322,9 +322,12 @@ def mask_stage_leg(dev, pk, img_size=550, img_h=480, img_w=640, reps=20):
     return out
 
 
-def training_leg(arch, img_size, per_gpu, steps, dev, rank, world):
+TRAIN_LR = 2e-4   # config.py:97 uses 2e-3 with warm-up on real data; random-init weights on random targets diverge at that rate within ~50 steps
+
+
+def training_leg(arch, img_size, per_gpu, steps, dev, rank, world, eager_only=False):
     """BASELINE.json configs[3]: res101_coco 550x550 training, bs per GPU = 2 (DDP 8x2 at N = 8), synthetic targets (3 boxes per image,
-    seed 1 + rank), SGD lr 0.002 momentum 0.9 wd 5e-4 (config.py:97-100), `steps` timed steps.  The step is Yolact.forward in train mode
+    seed 1 + rank), SGD lr TRAIN_LR momentum 0.9 wd 5e-4 (config.py:97-100), `steps` timed steps.  The step is Yolact.forward in train mode
     (native engine: forward + targets + losses) + loss.backward() (native backward) + optimizer.step(); under torchrun the module is
     wrapped in DistributedDataParallel (train.py:76) and the gradient all-reduce runs over NCCL.  Beside it, at N = 1: the same step
     on the reference's own GPU path (torch autograd over cuDNN: oracle/train_torch.py, TF32 default, cudnn.benchmark)."""
@@ -347,7 +350,7 @@ def training_leg(arch, img_size, per_gpu, steps, dev, rank, world):
 
     def run(net, fwd, n):
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=True) if world > 1 else net
-        opt = torch.optim.SGD(model.parameters(), lr=0.002, momentum=0.9, weight_decay=5e-4)
+        opt = torch.optim.SGD(model.parameters(), lr=TRAIN_LR, momentum=0.9, weight_decay=5e-4)
         first = None
 
         def step(_):
@@ -369,6 +372,13 @@ def training_leg(arch, img_size, per_gpu, steps, dev, rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), first
     try:
+        if eager_only:                                              # child process (see below)
+            torch.backends.cudnn.benchmark = True
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            ems, efirst = run(make(), lambda m: tt.training_step_forward(m, img, tgt, mks), max(5, steps // 5))
+            return {'impl': 'torch autograd over cuDNN / ATen (oracle/train_torch.py: the reference training branch restated), TF32, cudnn.benchmark',
+                    'img_per_s': per_gpu / (ems / 1e3), 'ms_per_step': ems, 'first_step_losses': efirst}
         net = make()
         ms, first = run(net, lambda m: m(img, tgt, mks), steps)
         out.update(value=world * per_gpu / (ms / 1e3), unit='img/s', ms_per_step=ms, first_step_losses=first, dtype='bf16 tensor-core operands, f32 accumulation / statistics / master weights',
@@ -376,18 +386,18 @@ def training_leg(arch, img_size, per_gpu, steps, dev, rank, world):
         del net
         torch.cuda.empty_cache()
         if world == 1:
-            prev = torch.backends.cudnn.benchmark
-            torch.backends.cudnn.benchmark = True
-            torch.backends.cudnn.allow_tf32 = True
-            torch.backends.cuda.matmul.allow_tf32 = True
-            ref = make()
-            ems, efirst = run(ref, lambda m: tt.training_step_forward(m, img, tgt, mks), max(5, steps // 5))
-            torch.backends.cudnn.benchmark = prev
-            out['gpu_eager_baseline'] = {'impl': 'torch autograd over cuDNN / ATen (oracle/train_torch.py: the reference training branch restated), TF32, cudnn.benchmark',
-                                         'img_per_s': per_gpu / (ems / 1e3), 'ms_per_step': ems, 'first_step_losses': efirst,
-                                         'ours_over_eager': (per_gpu / (ms / 1e3)) / (per_gpu / (ems / 1e3))}
-            del ref
-            torch.cuda.empty_cache()
+            # the eager baseline runs in a CHILD process: ATen's loss kernels device-assert on a NaN (a diverged run), and a device-side
+            # assert would take this process's CUDA context -- and every later leg of the bench line -- with it
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--eager-train-leg', '--arch', arch, '--img', str(img_size), '--batch', str(per_gpu),
+                                '--steps', str(steps)], capture_output=True, text=True, timeout=600)
+            js = [l for l in r.stdout.splitlines() if l.startswith('{')]
+            if r.returncode == 0 and js:
+                eb = json.loads(js[-1])
+                eb['ours_over_eager'] = (per_gpu / (ms / 1e3)) / eb['img_per_s']
+                out['gpu_eager_baseline'] = eb
+            else:
+                out['gpu_eager_baseline'] = {'error': (r.stderr or r.stdout)[-300:]}
     except Exception as e:
         out['error'] = repr(e)[:400]
     return out
@@ -565,26 +575,52 @@ def run_ours(args):
         # the package's public calls with the collective inside: pinned host -> device -> forward -> post-process -> all-gather -> D2H
         b = per_gpu[main_mode]
 
-        def e2e_step(i):
-            x = host[i & 1][:b].to(dev, non_blocking=True)
+        # software pipeline, as the single-GPU C entry points do it: the H2D copy of batch i+1 runs on a copy stream under the compute of
+        # batch i, and the gathered records of batch i-1 are read back after batch i has been launched
+        main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+        xbuf = [torch.empty(b, 3, IMG, IMG, device=dev) for _ in range(2)]
+        ev_up = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(ev_free[i & 1])                            # the forward that read this buffer last has finished with it
+                xbuf[i & 1].copy_(host[i & 1][:b], non_blocking=True)
+                ev_up[i & 1].record(copy_s)
+
+        def launch(i):
+            main_s.wait_event(ev_up[i & 1])
             with torch.no_grad():
-                o = net(x)
+                o = net(xbuf[i & 1])
+            ev_free[i & 1].record(main_s)
             d_ = detect_batched(o[0], o[1], o[2], anchors, cfg)
-            g = ydist.gather_detections(d_, async_op=True)
-            return g.wait().out.cpu()                                        # D2H of the gathered records (synchronises)
-        for i in range(3):
-            e2e_step(i)
+            return ydist.gather_detections(d_, async_op=True)
+
+        def e2e_run(n):
+            for e in ev_free:
+                e.record(main_s)
+            upload(0)
+            prev = None
+            for i in range(n):
+                if i + 1 < n:
+                    upload(i + 1)
+                g = launch(i)
+                if prev is not None:
+                    prev.wait().out.cpu()                                    # D2H of the gathered records (synchronises)
+                prev = g
+            return prev.wait().out.cpu()
+        e2e_run(3)
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for i in range(K):
-            e2e_step(i)
+        e2e_run(K)
         torch.cuda.synchronize()
         t = torch.tensor([time.perf_counter() - t0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {'value': world * b * K / float(t.item()), 'unit': 'img/s', 'h2d_bytes_per_step': b * 3 * IMG * IMG * 4,
                'd2h_bytes_per_step': world * b * (4 + D * (4 + 4 + 4 + 16 + 128)),
-               'api': 'pinned host tensor -> Yolact.forward -> detect_batched -> dist.gather_detections (NCCL) -> D2H of the gathered records'}
+               'api': 'pinned host tensor -> (copy stream) device -> Yolact.forward -> detect_batched -> dist.gather_detections (NCCL, async) -> D2H of the gathered records; '
+                      'two batches in flight'}
 
     training = None
     if world > 1 and not os.environ.get('YB_BENCH_QUICK') and (ARCH, IMG) == ('res101', 550):
@@ -711,6 +747,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--precision', default=os.environ.get('YOLACT_B200_PRECISION', 'fp16'), choices=['fp16', 'bf16', 'fp32'])
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--eager-train-leg', action='store_true', help=argparse.SUPPRESS)     # internal: training_leg's eager baseline in a child process
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='N > 1: images per GPU fixed at --batch (weak) or global batch fixed (strong); '
                     'the other mode is measured in the same run and reported beside it')
     ap.add_argument('--arch', default=ARCH, choices=['res101', 'res50', 'swin_tiny'], help='default: the BASELINE metric config')
@@ -718,6 +755,10 @@ if __name__ == '__main__':
     ap.add_argument('--batch', type=int, default=BATCH, help='images per GPU (weak) / global batch (strong)')
     args = ap.parse_args()
     ARCH, IMG, BATCH = args.arch, args.img, args.batch
+    if args.eager_train_leg:
+        import torch
+        print(json.dumps(training_leg(args.arch, args.img, args.batch, args.steps, torch.device('cuda', 0), 0, 1, eager_only=True)))
+        sys.exit(0)
     if args.impl == 'reference':
         run_reference(args)
     else:
