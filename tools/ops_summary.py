@@ -10,10 +10,15 @@ groups = collections.OrderedDict()
 for a in agg.values():
     ms = a['ms'] / a['n']
     kind = int(a['kind'])
-    key = KIND[kind] if kind != 3 else 'conv %sx%s s%s %4s->%4s @%3s' % (a['k'], a['k'], a['stride'], a['cin'], a['cout'], a['h_out'])
+    if kind == 11:                                                     # OP_BNECK: conv3 (cin -> cout) + residual chained into the next conv1 (cout -> cin)
+        key = 'fused 1x1 %4s->%4s + res, 1x1 ->%4s @%3s' % (a['cin'], a['cout'], a['cin'], a['h_out'])
+    elif kind == 3:
+        key = 'conv %sx%s s%s %4s->%4s @%3s' % (a['k'], a['k'], a['stride'], a['cin'], a['cout'], a['h_out'])
+    else:
+        key = KIND.get(kind, 'kind %d' % kind)
     g = groups.setdefault(key, dict(ms=0.0, n=0, gf=0.0, batch=a['batch']))
     g['ms'] += ms; g['n'] += 1; g['gf'] += float(a['gflop'])
 tot = sum(g['ms'] for g in groups.values())
 print(f'forward total {tot:.3f} ms over {len(agg)} layers')
 for key, g in sorted(groups.items(), key=lambda kv: -kv[1]['ms']):
-    print('%-34s n=%2d  %7.3f ms  %5.1f%%  %7.0f TFLOP/s' % (key, g['n'], g['ms'], 100 * g['ms'] / tot, g['gf'] / g['ms'] if g['ms'] else 0))
+    print('%-42s n=%2d  %7.3f ms  %5.1f%%  %7.0f TFLOP/s' % (key, g['n'], g['ms'], 100 * g['ms'] / tot, g['gf'] / g['ms'] if g['ms'] else 0))
