@@ -15,12 +15,14 @@ from oracle import synth, forward_torch as ft
 pytestmark = pytest.mark.gpu
 
 
-def _outputs(arch, S, B, precision, cuda, fuse):
+def _outputs(arch, S, B, precision, cuda, fuse, env=None):
     from yolact_minimal_b200.config import make_config
     from yolact_minimal_b200.modules.yolact import Yolact
     old = os.environ.pop('YOLACT_B200_NO_FUSE', None)
     if not fuse:
         os.environ['YOLACT_B200_NO_FUSE'] = '1'
+    for k, v in (env or {}).items():
+        os.environ[k] = v
     try:
         cfg = make_config(arch + '_coco', S)
         cfg.precision, cfg.max_batch = precision, B
@@ -35,6 +37,8 @@ def _outputs(arch, S, B, precision, cuda, fuse):
         launches = net.engine(B).launches_per_forward() if hasattr(net.engine(B), 'launches_per_forward') else None
         torch.cuda.synchronize()
     finally:
+        for k in (env or {}):
+            os.environ.pop(k, None)
         os.environ.pop('YOLACT_B200_NO_FUSE', None)
         if old is not None:
             os.environ['YOLACT_B200_NO_FUSE'] = old
@@ -51,3 +55,14 @@ def test_fused_equals_unfused_bitwise(cuda, arch, S, B, precision):
         assert torch.equal(a, c), name                                   # deterministic run to run
         assert torch.equal(a, b), (name, float((a - b).abs().max()))
     assert np.isfinite(fused[0].cpu().numpy()).all()
+
+
+@pytest.mark.parametrize('arch,S,B', [('res50', 128, 2), ('res101', 550, 3)])
+def test_stem_on_pixel_rows_equals_overlapping_rows_bitwise(cuda, arch, S, B):
+    """The stem convolution on 32-byte pixel rows (one slab per tap row, the dx taps as row-shifted K = 16 MMAs) issues the same MMAs in the
+    same order as the overlapping-rows K = 64 form it replaced (YOLACT_B200_NO_STEM16=1): the network output must not change by a bit."""
+    new, _, c4n, _ = _outputs(arch, S, B, 'fp16', cuda, True)
+    old, _, c4o, _ = _outputs(arch, S, B, 'fp16', cuda, True, env={'YOLACT_B200_NO_STEM16': '1'})
+    assert torch.equal(c4n, c4o), float((c4n - c4o).abs().max())
+    for name, a, b in zip(('cls', 'box', 'coef', 'proto'), new, old):
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
