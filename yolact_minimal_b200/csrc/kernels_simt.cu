@@ -316,22 +316,36 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_phase_split(const T* __restrict__ in, T* __restrict__ out, int B, int C, int Hin, int Hout,
                                                      long long plane_stride_rows) {
   constexpr int N = VecIO<T>::N;
+  constexpr int kPx = 4;                                               // output pixels per thread: four independent 16-byte loads in flight
   const int Hpi = Hin + 2, Hpo = Hout + 2, CV = C / N;
+  const int nq = (Hpo + kPx - 1) / kPx;
   const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= Hpo * CV) return;
-  const int xp = t / CV, cv = t - xp * CV, yp = blockIdx.y;
+  if (t >= nq * CV) return;
+  const int xq = t / CV, cv = t - xq * CV, yp = blockIdx.y;
   const int pl = blockIdx.z / B, b = blockIdx.z - pl * B;
   const int p = pl >> 1, q = pl & 1;
-  const int iy = 2 * (yp - 1) + p, ix = 2 * (xp - 1) + q;
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (iy >= 0 && iy < Hin && ix >= 0 && ix < Hin) v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * Hpi + iy + 1) * Hpi + ix + 1) * C + cv * N));
-  *reinterpret_cast<uint4*>(out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo + xp) * C + cv * N) = v;
+  const int iy = 2 * (yp - 1) + p;
+  const bool row_ok = iy >= 0 && iy < Hin;
+  const T* irow = in + (((size_t)b * Hpi + iy + 1) * Hpi + 1) * C + cv * N;
+  T* orow = out + ((size_t)pl * plane_stride_rows + ((size_t)b * Hpo + yp) * Hpo) * C + cv * N;
+  uint4 v[kPx];
+#pragma unroll
+  for (int i = 0; i < kPx; ++i) {
+    const int xp = xq * kPx + i, ix = 2 * (xp - 1) + q;
+    v[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (row_ok && xp < Hpo && ix >= 0 && ix < Hin) v[i] = __ldg(reinterpret_cast<const uint4*>(irow + (size_t)ix * C));
+  }
+#pragma unroll
+  for (int i = 0; i < kPx; ++i) {
+    const int xp = xq * kPx + i;
+    if (xp < Hpo) *reinterpret_cast<uint4*>(orow + (size_t)xp * C) = v[i];
+  }
 }
 
 int launch_phase_split(const void* in, void* out, int dt, int B, int C, int Hin, int Hout, int nplanes,
                        long long plane_stride_rows, cudaStream_t s) {
   const int cv = C / (dt == DT_F32 ? 4 : 8);
-  dim3 grid(ceil_div((Hout + 2) * cv, 256), Hout + 2, B * nplanes);
+  dim3 grid(ceil_div(((Hout + 2 + 3) / 4) * cv, 256), Hout + 2, B * nplanes);
   YB_DISPATCH_DT(dt, (k_phase_split<T><<<grid, 256, 0, s>>>((const T*)in, (T*)out, B, C, Hin, Hout, plane_stride_rows)));
   YB_CHECK_LAUNCH();
   return YB_OK;
