@@ -843,7 +843,10 @@ constexpr uint32_t BK_SLOT = 16384;
 struct BnParams {
   long long M;
   int m_tiles;              // pair tiles of 256 rows
-  int Cmid, Cexp, nchunks, kbA;
+  int Cmid, Cexp, nchunks, kbA;   // kbA: k-blocks of GEMM A = (Cmid + Cd) / 64
+  int kbT;                  // of which from t2 (Cmid / 64); the rest from xd (the block's input, see has_res)
+  int has_res;              // 1: residual x added through identity MMAs;  0: the residual branch is a 1x1 convolution of xd folded INTO GEMM A
+                            // (first block of a stage: W3 and the downsample weights side by side along K, biases summed)
   int slots;                // ring depth (5..8 slots of 16 KB, whatever shared memory is left)
   int t2_bufs;              // 2: the next tile's t2 is loaded while this one is in use (narrow layers are HBM-latency bound otherwise)
   unsigned long long* trace;  // tooling (YOLACT_B200_BNECK_TRACE): cycle stamps, see k_bneck_tc
@@ -854,9 +857,9 @@ struct BnParams {
 
 template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW3,
-           const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmXo, const __grid_constant__ CUtensorMap tmT1,
-           const BnParams p) {
+k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUtensorMap tmXd, const __grid_constant__ CUtensorMap tmX,
+           const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmXo,
+           const __grid_constant__ CUtensorMap tmT1, const BnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t rank = cluster_ctarank();
@@ -945,7 +948,7 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
             tma_load_2d_pair(sRing + (size_t)stage * BK_SLOT + (size_t)j * 8192, &tmW3, (kpb * s + j) * TC_BK, c * 128 + (int)rank * 64, fa);
           if (++stage == slots) { stage = 0; phase ^= 1; }
         }
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 2 && p.has_res; ++j) {
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t fa = map_to_rank(smem_u32(&full[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * BK_SLOT);
@@ -969,7 +972,8 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
         mbar_wait(&t2_empty[tb], (tn & 1u) ^ 1u);                        // A(last) of the tile that used it before has read it
         if (rank == 0) mbar_expect_tx(&t2_full[tb], 2u * (uint32_t)kbA * TC_A_STAGE);
         const uint32_t t2_full_addr = map_to_rank(smem_u32(&t2_full[tb]), 0);
-        for (int kb = 0; kb < kbA; ++kb) tma_load_2d_pair(sT2 + ((size_t)tb * kbA + kb) * TC_A_STAGE, &tmT2, kb * TC_BK, row0, t2_full_addr);
+        for (int kb = 0; kb < kbA; ++kb)                                 // A tile of GEMM A: t2's k-blocks, then the block input's (if folded in)
+          tma_load_2d_pair(sT2 + ((size_t)tb * kbA + kb) * TC_A_STAGE, kb < p.kbT ? &tmT2 : &tmXd, (kb < p.kbT ? kb : kb - p.kbT) * TC_BK, row0, t2_full_addr);
         for (int c = 0; c < nch; ++c) {
           load_a(c, row0);
           if (c >= 1) load_b(c - 1);
@@ -1032,7 +1036,7 @@ k_bneck_tc(const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUt
             umma_commit_pair(&empty[stage], issue);
             if (++stage == slots) { stage = 0; phase ^= 1; }
           }
-          for (int j = 0; j < 2; ++j) {                                 // accA[:, 64j .. 64j+63] += x_j * I
+          for (int j = 0; j < 2 && p.has_res; ++j) {                    // accA[:, 64j .. 64j+63] += x_j * I
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint64_t da = umma_desc(smem_u32(sRing + (size_t)stage * BK_SLOT));
@@ -1495,8 +1499,8 @@ int launch_conv_tc(const TcPlan* pl, const ConvArgs& a, cudaStream_t s) {
 
 // ---- fused bottleneck tail (k_bneck_tc) ------------------------------------------------------------------------------
 struct BnPlan {
-  CUtensorMap tmT2, tmX, tmW3, tmW1, tmXo, tmT1;
-  int sms, Cmid, Cexp, slots, t2_bufs;
+  CUtensorMap tmT2, tmXd, tmX, tmW3, tmW1, tmXo, tmT1;
+  int sms, Cmid, Cexp, Cd, slots, t2_bufs;
   size_t smem_bytes;
 };
 
@@ -1507,8 +1511,8 @@ bool bneck_supported(int act_dt, int Cmid, int Cexp) {
 }
 
 // shared-memory plan: [t2 buffers][x' staging 64 KB][ring][identity 4 KB][biases][barriers]
-static void bneck_smem(int Cmid, int Cexp, int* slots, int* t2_bufs, size_t* bytes) {
-  const size_t t2 = (size_t)(Cmid / 64) * TC_A_STAGE;
+static void bneck_smem(int Cmid, int Cexp, int Cd, int* slots, int* t2_bufs, size_t* bytes) {
+  const size_t t2 = (size_t)((Cmid + Cd) / 64) * TC_A_STAGE;
   const size_t fixed = 1024 + 4 * TC_A_STAGE + 4096 + (size_t)(Cexp + Cmid) * 4 + 1024;
   const size_t budget = 227 * 1024;
   *t2_bufs = (fixed + 2 * t2 + 5 * BK_SLOT <= budget) ? 2 : 1;
@@ -1520,19 +1524,23 @@ static void bneck_smem(int Cmid, int Cexp, int* slots, int* t2_bufs, size_t* byt
 int bneck_plan_create(const BneckArgs& a, int max_batch, BnPlan** out) {
   YB_REQUIRE(bneck_supported(a.act_dt, a.Cmid, a.Cexp), YB_ERR_UNSUPPORTED, "bneck_plan_create: unsupported Cmid=%d Cexp=%d", a.Cmid, a.Cexp);
   BnPlan* pl = new BnPlan();
-  pl->Cmid = a.Cmid; pl->Cexp = a.Cexp;
+  pl->Cmid = a.Cmid; pl->Cexp = a.Cexp; pl->Cd = a.Cd;
+  YB_REQUIRE(a.Cd == 0 || (a.xd && a.Cd % 64 == 0 && (a.Cmid + a.Cd) / 64 <= 2), YB_ERR_UNSUPPORTED, "bneck_plan_create: folded residual branch with Cd=%d", a.Cd);
+  YB_REQUIRE(a.Cd != 0 || a.x, YB_ERR_INVALID, "bneck_plan_create: no residual");
   const bool f16 = a.act_dt == DT_F16;
   const uint64_t rows = (uint64_t)max_batch * a.g.plane();
   int s = make_map(&pl->tmT2, a.t2, (uint64_t)a.Cmid, rows, TC_BM, f16);
-  if (s == YB_OK) s = make_map(&pl->tmX, a.x, (uint64_t)a.Cexp, rows, TC_BM, f16);
-  if (s == YB_OK) s = make_map(&pl->tmW3, a.w3, (uint64_t)a.Cmid, (uint64_t)a.Cexp, 64, f16);
+  pl->tmXd = pl->tmT2; pl->tmX = pl->tmT2;                        // placeholders for the operand a form does not have
+  if (s == YB_OK && a.Cd) s = make_map(&pl->tmXd, a.xd, (uint64_t)a.Cd, rows, TC_BM, f16);
+  if (s == YB_OK && !a.Cd) s = make_map(&pl->tmX, a.x, (uint64_t)a.Cexp, rows, TC_BM, f16);
+  if (s == YB_OK) s = make_map(&pl->tmW3, a.w3, (uint64_t)(a.Cmid + a.Cd), (uint64_t)a.Cexp, 64, f16);
   if (s == YB_OK) s = make_map(&pl->tmW1, a.w1, (uint64_t)a.Cexp, (uint64_t)a.Cmid, (uint32_t)(a.Cmid / 2), f16);
   if (s == YB_OK) s = make_map(&pl->tmXo, a.xo, (uint64_t)a.Cexp, rows, 32, f16);
   if (s == YB_OK) s = a.Cmid >= 128 ? make_map(&pl->tmT1, a.t1, (uint64_t)a.Cmid, rows, 32, f16)
                                     : make_map(&pl->tmT1, a.t1, (uint64_t)a.Cmid, rows, 32, f16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (s == YB_OK) s = tc_device_setup(&pl->sms);
   if (s != YB_OK) { delete pl; return s; }
-  bneck_smem(a.Cmid, a.Cexp, &pl->slots, &pl->t2_bufs, &pl->smem_bytes);
+  bneck_smem(a.Cmid, a.Cexp, a.Cd, &pl->slots, &pl->t2_bufs, &pl->smem_bytes);
   YB_REQUIRE(pl->slots >= 5 && pl->smem_bytes <= 227 * 1024, YB_ERR_UNSUPPORTED, "bneck_plan_create: %zu bytes of shared memory, %d slots", pl->smem_bytes, pl->slots);
   *out = pl;
   return YB_OK;
@@ -1546,7 +1554,7 @@ int launch_bneck_tc(const BnPlan* pl, const BneckArgs& a, cudaStream_t s) {
   BnParams p;
   p.M = (long long)a.B * a.g.plane();
   p.m_tiles = (int)((p.M + 2 * TC_BM - 1) / (2 * TC_BM));
-  p.Cmid = a.Cmid; p.Cexp = a.Cexp; p.nchunks = a.Cexp / 128; p.kbA = a.Cmid / 64;
+  p.Cmid = a.Cmid; p.Cexp = a.Cexp; p.nchunks = a.Cexp / 128; p.kbT = a.Cmid / 64; p.kbA = (a.Cmid + pl->Cd) / 64; p.has_res = pl->Cd ? 0 : 1;
   p.slots = pl->slots; p.t2_bufs = pl->t2_bufs;
   p.g = a.g; p.b3 = a.b3; p.b1 = a.b1;
   p.trace = nullptr;
@@ -1572,8 +1580,8 @@ int launch_bneck_tc(const BnPlan* pl, const BneckArgs& a, cudaStream_t s) {
   ++na;
   cfg.attrs = attr; cfg.numAttrs = na;
   const cudaError_t le = a.act_dt == DT_F16
-      ? cudaLaunchKernelEx(&cfg, k_bneck_tc<true>, pl->tmT2, pl->tmX, pl->tmW3, pl->tmW1, pl->tmXo, pl->tmT1, p)
-      : cudaLaunchKernelEx(&cfg, k_bneck_tc<false>, pl->tmT2, pl->tmX, pl->tmW3, pl->tmW1, pl->tmXo, pl->tmT1, p);
+      ? cudaLaunchKernelEx(&cfg, k_bneck_tc<true>, pl->tmT2, pl->tmXd, pl->tmX, pl->tmW3, pl->tmW1, pl->tmXo, pl->tmT1, p)
+      : cudaLaunchKernelEx(&cfg, k_bneck_tc<false>, pl->tmT2, pl->tmXd, pl->tmX, pl->tmW3, pl->tmW1, pl->tmXo, pl->tmT1, p);
   YB_CHECK_CUDA(le);
   YB_CHECK_LAUNCH();
   return YB_OK;

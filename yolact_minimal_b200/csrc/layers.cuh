@@ -82,8 +82,11 @@ int launch_gemm_tc(const TcPlan* p, const GemmArgs& g, cudaStream_t s);
 //   xo = relu(W3 * t2 + b3 + x)            1x1 Cmid -> Cexp, residual x, written out (the next block's residual / the stage output)
 //   t1 = relu(W1 * xo + b1)                1x1 Cexp -> Cmid of the NEXT block, fed from shared memory: xo is never re-read from HBM
 // All four tensors are haloed NHWC with the same geometry; weights are the packed K-major matrices of the two convolutions.
+// First block of a stage (Cd > 0): the residual branch is itself a 1x1 convolution of the block input xd (Cd channels, same geometry);
+// it is folded into the first GEMM -- w3 is then [Cexp][Cmid + Cd] (conv3 | downsample weights side by side), b3 the summed biases, x unused.
 struct BneckArgs {
   const void* t2; const void* x; const void* w3; const void* w1;
+  const void* xd; int Cd;
   const float* b3; const float* b1;
   void* xo; void* t1;
   int act_dt, B, Cmid, Cexp;

@@ -59,6 +59,11 @@ struct Op {
   // OP_BNECK (fuse_bottlenecks): conv3 (`conv`, in, res -> out) of one bottleneck chained into conv1 (`conv2`, out -> out2) of the next
   int conv2 = -1, out2 = -1;
   BnPlan* bn = nullptr;
+  // ... and, for the first block of a stage, the 1x1 downsample convolution (`convd`, in2 -> the residual) folded into the first GEMM:
+  // weights of conv3 and downsample side by side along K (`d_wcat`), biases summed (`d_bcat`); no residual tensor exists any more
+  int convd = -1, in2 = -1;
+  void* d_wcat = nullptr;
+  float* d_bcat = nullptr;
 };
 
 }  // namespace
@@ -370,16 +375,36 @@ void fuse_bottlenecks(yb_net* net) {
     }
     merged.push_back(a);
   }
-  net->ops.swap(merged);
+  // first block of a stage whose residual branch is a stride-1 1x1 convolution of the block input (layer1): fold it into GEMM A
+  // when the concatenated K still fits the resident A tile (two k-blocks)
+  std::vector<Op> folded;
+  for (size_t i = 0; i < merged.size(); ++i) {
+    Op f = merged[i];
+    if (f.kind == OP_BNECK && !folded.empty() && !getenv("YOLACT_B200_NO_FUSE_DOWN")) {
+      const Op& d = folded.back();
+      if (d.kind == OP_CONV && d.out == f.res && d.stride == 1 && d.relu == 0 && d.res < 0 && d.out_mode == 0 && d.ext == EXT_NONE) {
+        const ConvW& cd = net->convs[d.conv];
+        const ConvW& c3 = net->convs[f.conv];
+        if (cd.k == 1 && cd.cat.empty() && cd.Cin == cd.Cin_pad && cd.Cout == c3.Cout && (c3.Cin + cd.Cin) / 64 <= 2 && net->acts[d.in].H == net->acts[f.in].H) {
+          f.convd = d.conv; f.in2 = d.in; f.res = -1;
+          folded.pop_back();                                         // the downsample launch and its output tensor are gone
+        }
+      }
+    }
+    folded.push_back(f);
+  }
+  net->ops.swap(folded);
 }
 
 void bneck_args(const yb_net* net, const Op& o, int B, BneckArgs* a) {
   const ConvW& c3 = net->convs[o.conv];
   const ConvW& c1 = net->convs[o.conv2];
   memset(a, 0, sizeof(*a));
-  a->t2 = net->slots[net->acts[o.in].slot]; a->x = net->slots[net->acts[o.res].slot];
+  a->t2 = net->slots[net->acts[o.in].slot];
+  if (o.convd >= 0) { a->xd = net->slots[net->acts[o.in2].slot]; a->Cd = net->convs[o.convd].Cin; }
+  else a->x = net->slots[net->acts[o.res].slot];
   a->xo = net->slots[net->acts[o.out].slot]; a->t1 = net->slots[net->acts[o.out2].slot];
-  a->w3 = c3.d_w; a->b3 = c3.d_b; a->w1 = c1.d_w; a->b1 = c1.d_b;
+  a->w3 = o.convd >= 0 ? o.d_wcat : c3.d_w; a->b3 = o.convd >= 0 ? o.d_bcat : c3.d_b; a->w1 = c1.d_w; a->b1 = c1.d_b;
   a->act_dt = net->act_dt; a->B = B; a->Cmid = c3.Cin; a->Cexp = c3.Cout;
   a->g.H = net->acts[o.in].H; a->g.W = a->g.H;
 }
@@ -390,7 +415,7 @@ void plan_memory(yb_net* net) {
   for (auto& a : acts) { a.first = 1 << 30; a.last = -1; }
   for (int i = 0; i < (int)net->ops.size(); ++i) {
     const Op& o = net->ops[i];
-    for (int t : {o.in, o.out, o.res, o.aux, o.out2}) {
+    for (int t : {o.in, o.out, o.res, o.aux, o.out2, o.in2}) {
       if (t < 0) continue;
       acts[t].first = acts[t].first < i ? acts[t].first : i;
       acts[t].last = acts[t].last > i ? acts[t].last : i;
@@ -544,7 +569,7 @@ extern "C" void yb_net_destroy(yb_net* net) {
   if (!net) return;
   for (void* p : net->slots) cudaFree(p);
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); }
-  for (auto& o : net->ops) { tc_plan_destroy(o.tc); bneck_plan_destroy(o.bn); }
+  for (auto& o : net->ops) { tc_plan_destroy(o.tc); bneck_plan_destroy(o.bn); cudaFree(o.d_wcat); cudaFree(o.d_bcat); }
   for (auto& kv : net->d_vec) cudaFree(kv.second);
   cudaFree(net->d_pe_w);
   for (void* p : {(void*)net->d_anchors, (void*)net->d_stem_w, (void*)net->d_stem_b, net->d_stem_w16, (void*)net->d_stem_b16, (void*)net->d_img, (void*)net->d_cls,
@@ -593,7 +618,7 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
   for (void* p : net->slots) cudaFree(p);
   net->slots.clear();
   for (auto& c : net->convs) { cudaFree(c.d_w); cudaFree(c.d_b); c.d_w = nullptr; c.d_b = nullptr; }
-  for (auto& o : net->ops) { tc_plan_destroy(o.tc); bneck_plan_destroy(o.bn); }
+  for (auto& o : net->ops) { tc_plan_destroy(o.tc); bneck_plan_destroy(o.bn); cudaFree(o.d_wcat); cudaFree(o.d_bcat); }
   net->ops = net->ops_base;
   cudaFree(net->d_anchors); cudaFree(net->d_stem_w); cudaFree(net->d_stem_b); cudaFree(net->d_stem_w16); cudaFree(net->d_stem_b16);
   net->d_anchors = net->d_stem_w = net->d_stem_b = net->d_stem_b16 = nullptr; net->d_stem_w16 = nullptr;
@@ -667,6 +692,19 @@ extern "C" int yb_net_finalize(yb_net* net, int max_batch, int precision) {
     }
     for (auto& o : net->ops) {
       if (o.kind == OP_BNECK) {
+        if (o.convd >= 0) {                                          // [Cexp][Cmid | Cd] 16-bit weights (both already BN-folded and rounded), b3 + bd
+          const ConvW& c3 = net->convs[o.conv];
+          const ConvW& cd = net->convs[o.convd];
+          const size_t esz = dtype_size(net->act_dt), ldc = (size_t)(c3.Cin + cd.Cin) * esz;
+          YB_CHECK_CUDA(cudaMalloc(&o.d_wcat, (size_t)c3.Cout * ldc));
+          YB_CHECK_CUDA(cudaMemcpy2D(o.d_wcat, ldc, c3.d_w, (size_t)c3.Cin * esz, (size_t)c3.Cin * esz, c3.Cout, cudaMemcpyDeviceToDevice));
+          YB_CHECK_CUDA(cudaMemcpy2D((char*)o.d_wcat + (size_t)c3.Cin * esz, ldc, cd.d_w, (size_t)cd.Cin * esz, (size_t)cd.Cin * esz, c3.Cout, cudaMemcpyDeviceToDevice));
+          std::vector<float> b3(c3.Cout), bd(c3.Cout);
+          YB_CHECK_CUDA(cudaMemcpy(b3.data(), c3.d_b, b3.size() * 4, cudaMemcpyDeviceToHost));
+          YB_CHECK_CUDA(cudaMemcpy(bd.data(), cd.d_b, bd.size() * 4, cudaMemcpyDeviceToHost));
+          for (size_t i = 0; i < b3.size(); ++i) b3[i] += bd[i];
+          YB_PROPAGATE(upload(b3.data(), b3.size() * 4, (void**)&o.d_bcat));
+        }
         BneckArgs b;
         bneck_args(net, o, max_batch, &b);
         YB_PROPAGATE(bneck_plan_create(b, max_batch, &o.bn));
@@ -834,6 +872,11 @@ extern "C" int yb_net_profile(yb_net* net, yb_prof_entry* out, int max_entries, 
           k = 12;
           flops = 4.0 * px * c3.Cout * c3.Cin;
           bytes = px * esz * (2.0 * c3.Cin + 2.0 * c3.Cout) + 2.0 * c3.Cout * c3.Cin * esz;
+          if (o.convd >= 0) {                                          // + the folded downsample conv; its output / the residual read do not exist
+            const double Cd = net->convs[o.convd].Cin;
+            flops += 2.0 * px * c3.Cout * Cd;
+            bytes += px * esz * (Cd - c3.Cout) + c3.Cout * Cd * esz;
+          }
           break;
         }
         case OP_STEM: k = 2; flops = 2.0 * B * net->H1 * net->H1 * 64 * 147; bytes = B * 3.0 * net->cfg.img_size * net->cfg.img_size * 4 + B * net->H1 * net->H1 * 64.0 * esz; break;
