@@ -510,13 +510,18 @@ int launch_upsample2x_ac(const void* in, void* out, int dt, int B, int C, int Hi
   const int cv = C / (dt == DT_F32 ? 4 : 8);
   const size_t smem = (size_t)kUpTY * kUpSX * C * 4;
   if (dt != DT_F32 && smem <= 100 * 1024 && C % 8 == 0 && 256 % cv == 0 && cv <= 32) {
-    static std::once_flag once;
-    static cudaError_t attr = cudaSuccess;
-    std::call_once(once, [] {
-      attr = cudaFuncSetAttribute(k_upsample2x_tile<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      if (attr == cudaSuccess) attr = cudaFuncSetAttribute(k_upsample2x_tile<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    });
-    YB_CHECK_CUDA(attr);
+    {  // function attributes are per device: set once for the device this launch runs on
+      static std::mutex mu;
+      static bool done[64] = {};
+      int dev = 0;
+      YB_CHECK_CUDA(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lock(mu);
+      if (dev >= 0 && dev < 64 && !done[dev]) {
+        YB_CHECK_CUDA(cudaFuncSetAttribute(k_upsample2x_tile<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        YB_CHECK_CUDA(cudaFuncSetAttribute(k_upsample2x_tile<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        done[dev] = true;
+      }
+    }
     dim3 grid(ceil_div(Hout + 2, kUpTX), ceil_div(Hout + 2, kUpTY), B);
     if (dt == DT_F16) k_upsample2x_tile<__half><<<grid, 256, smem, s>>>((const __half*)in, (__half*)out, C, Hin, Hout, scale);
     else k_upsample2x_tile<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, C, Hin, Hout, scale);
